@@ -1,0 +1,227 @@
+// Bandwidth-bound helper kernels of the SR3 step (everything that is not a tensor-core tile):
+// GroupNorm apply (+SiLU) with channel concat, fp32->bf16 cast / nearest 2x upsample, row softmax,
+// noise-level embedding MLP + FiLM projections, weight packing, layout conversion at the API boundary.
+#pragma once
+#include "gemm_tcgen05.cuh"
+
+namespace sr3 {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&lo);
+    u.y = *reinterpret_cast<uint32_t*>(&hi);
+    return u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm apply: a = [silu]( (x - mean_g) * rstd_g * gamma_c + beta_c ), x = concat(src0, src1) along channels.
+// Statistics come from the per-(image, channel) sums the producing GEMM epilogues accumulated.
+// reference: nn.GroupNorm(groups, C, eps=1e-5) + Swish of Block (unet.py:80-91), torch.cat of unet.py:255.
+struct PrepParams {
+    const float* src0; const float* src1;
+    const float* st0; const float* st1;     // [B][C0][2], [B][C1][2]
+    int C0, C1;
+    const float* gamma; const float* beta;
+    int groups, HW, pix_per_block, silu;
+    float eps;
+    __nv_bfloat16* out_a;                   // [B][HW][C0+C1]
+    __nv_bfloat16* out_raw;                 // optional bf16(x), same shape
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
+    extern __shared__ float sm[];
+    const int C = p.C0 + p.C1;
+    float* sc = sm;              // [C]
+    float* sh = sm + C;          // [C]
+    float* gm = sm + 2 * C;      // [groups] mean
+    float* gr = gm + p.groups;   // [groups] rstd
+    const int b = blockIdx.y;
+    const int gs = C / p.groups;
+    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+        float s = 0.f, q = 0.f;
+        for (int j = 0; j < gs; ++j) {
+            const int c = g * gs + j;
+            const float* st = (c < p.C0) ? p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2
+                                         : p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2;
+            s += st[0]; q += st[1];
+        }
+        const float inv = 1.0f / (static_cast<float>(gs) * static_cast<float>(p.HW));
+        const float mean = s * inv;
+        const float var = fmaxf(q * inv - mean * mean, 0.f);
+        gm[g] = mean; gr[g] = rsqrtf(var + p.eps);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const float k = gr[g] * p.gamma[c];
+        sc[c] = k; sh[c] = p.beta[c] - gm[g] * k;
+    }
+    __syncthreads();
+    const int vec_per_pix = C >> 2;
+    const int pix0 = blockIdx.x * p.pix_per_block;
+    const int npix = min(p.pix_per_block, p.HW - pix0);
+    const int total = npix * vec_per_pix;
+    for (int i = threadIdx.x; i < total; i += blockDim.x) {
+        const int pix = pix0 + i / vec_per_pix;
+        const int c = (i % vec_per_pix) << 2;
+        const long long pg = static_cast<long long>(b) * p.HW + pix;
+        float4 x;
+        if (c < p.C0) x = __ldg(reinterpret_cast<const float4*>(p.src0 + pg * p.C0 + c));
+        else x = __ldg(reinterpret_cast<const float4*>(p.src1 + pg * p.C1 + (c - p.C0)));
+        float y0 = x.x * sc[c] + sh[c], y1 = x.y * sc[c + 1] + sh[c + 1], y2 = x.z * sc[c + 2] + sh[c + 2], y3 = x.w * sc[c + 3] + sh[c + 3];
+        if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+        *reinterpret_cast<uint2*>(p.out_a + pg * C + c) = pack_bf16x4(y0, y1, y2, y3);
+        if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + pg * C + c) = pack_bf16x4(x.x, x.y, x.z, x.w);
+    }
+}
+
+// fp32 NHWC -> bf16 NHWC, optionally nearest-2x upsampled (nn.Upsample(scale_factor=2,'nearest'), unet.py:58-65)
+__global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W,
+                                                   int C, int up) {
+    const int OH = H * up, OW = W * up;
+    const long long total = static_cast<long long>(B) * OH * OW * (C >> 2);
+    const int vpp = C >> 2;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int v = static_cast<int>(i % vpp);
+        long long pix = i / vpp;
+        const int ow = static_cast<int>(pix % OW); pix /= OW;
+        const int oh = static_cast<int>(pix % OH);
+        const int b = static_cast<int>(pix / OH);
+        const long long sp = (static_cast<long long>(b) * H + oh / up) * W + ow / up;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src + sp * C + (v << 2)));
+        *reinterpret_cast<uint2*>(dst + i * 4) = pack_bf16x4(x.x, x.y, x.z, x.w);
+    }
+}
+
+// Row softmax over keys (torch.softmax(attn, -1), unet.py:136): S fp32 [rows][L] -> P bf16 [rows][L].
+// Rows are grouped in segments of `seg` tokens; a row only attends to the keys of its own segment (two 64-token images share
+// one 128-row attention batch); keys outside get probability 0.
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows, int L,
+                                                      int seg) {
+    const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int r_in = static_cast<int>(row % L);
+    const int k0 = (r_in / seg) * seg;
+    const float* s = S + row * L;
+    __nv_bfloat16* pr = P + row * L;
+    float m = -INFINITY;
+    for (int k = k0 + lane; k < k0 + seg; k += 32) m = fmaxf(m, s[k]);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int k = k0 + lane; k < k0 + seg; k += 32) sum += expf(s[k] - m);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.0f / sum;
+    for (int k = lane; k < L; k += 32) {
+        const float v = (k >= k0 && k < k0 + seg) ? expf(s[k] - m) * inv : 0.f;
+        pr[k] = __float2bfloat16_rn(v);
+    }
+}
+
+// Start of a step: clear the GroupNorm statistics arena and advance the device-side timestep.
+__global__ void __launch_bounds__(256) step_begin_kernel(float4* stats, long long n4, StepCtl* ctl) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x)
+        stats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int t = ctl->t_next;
+        ctl->t_cur = t;
+        ctl->t_next = t - 1;
+    }
+}
+
+// PositionalEncoding + noise_level_mlp (unet.py:18-31, 177-184): one block per image -> tau[b][inner].
+struct EmbedParams {
+    const StepCtl* ctl;
+    const float* nl_table;   // fp32(sqrt_alphas_cumprod_prev) [T+1]
+    const float* nl_buf;     // [B]
+    const float* w1; const float* b1;   // [4*inner][inner]
+    const float* w2; const float* b2;   // [inner][4*inner]
+    float* tau;              // [B][inner]
+    int inner;
+};
+__global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
+    extern __shared__ float sm[];
+    const int inner = p.inner, hid = 4 * inner;
+    float* pe = sm;            // [inner]
+    float* h = sm + inner;     // [hid]
+    const int b = blockIdx.x;
+    const float nl = p.ctl->nl_from_table ? p.nl_table[p.ctl->t_cur + 1] : p.nl_buf[b];
+    const int count = inner / 2;
+    for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+        const int jj = j < count ? j : j - count;
+        const float step = static_cast<float>(jj) / static_cast<float>(count);
+        const float e = nl * expf(-9.210340371976184f * step);
+        pe[j] = j < count ? sinf(e) : cosf(e);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
+        float a = p.b1[j];
+        for (int i = 0; i < inner; ++i) a += p.w1[j * inner + i] * pe[i];
+        h[j] = a / (1.0f + expf(-a));
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+        float a = p.b2[j];
+        for (int i = 0; i < hid; ++i) a += p.w2[j * hid + i] * h[i];
+        p.tau[b * inner + j] = a;
+    }
+}
+
+// All FeatureWiseAffine projections at once (unet.py:34-50, bias-only form) + the block1 conv bias folded in:
+// film[b][j] = Wf[j] . tau[b] + bf[j] + cbias[j],  j over the concatenated Cout of every ResnetBlock.
+__global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ wf, const float* __restrict__ bf, const float* __restrict__ cbias,
+                                                   const float* __restrict__ tau, float* __restrict__ film, int F, int inner) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.y;
+    if (j >= F) return;
+    float a = bf[j] + cbias[j];
+    const float* w = wf + static_cast<long long>(j) * inner;
+    const float* t = tau + b * inner;
+    for (int i = 0; i < inner; ++i) a += w[i] * t[i];
+    film[static_cast<long long>(b) * F + j] = a;
+}
+
+// OIHW fp32 conv weight -> K-major bf16 GEMM operand: dst[o][k_off + (r*KW+s)*cin_pad + c]
+__global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
+                                                               int KH, int KW, int ktot, int k_off, int cin_pad) {
+    const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int s = static_cast<int>(r % KW); r /= KW;
+        const int rr = static_cast<int>(r % KH); r /= KH;
+        const int c = static_cast<int>(r % Cin);
+        const int o = static_cast<int>(r / Cin);
+        dst[static_cast<long long>(o) * ktot + k_off + (rr * KW + s) * cin_pad + c] = __float2bfloat16_rn(src[i]);
+    }
+}
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+// API boundary: NCHW fp32 (reference layout) -> bf16 NHWC channel slice of the UNet input buffer (+ optional fp32 NCHW copy).
+__global__ void __launch_bounds__(256) load_nchw_kernel(const float* __restrict__ src, int B, int C, int H, int W, __nv_bfloat16* __restrict__ in_buf,
+                                                        int in_C, int coff, float* __restrict__ copy) {
+    const long long total = static_cast<long long>(B) * C * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int w = static_cast<int>(r % W); r /= W;
+        const int h = static_cast<int>(r % H); r /= H;
+        const int c = static_cast<int>(r % C);
+        const int b = static_cast<int>(r / C);
+        const float v = src[i];
+        in_buf[((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c] = __float2bfloat16_rn(v);
+        if (copy) copy[i] = v;
+    }
+}
+
+}  // namespace sr3

@@ -1,0 +1,1037 @@
+// Host side of libsr3_b200.so: builds the per-step kernel plan of the SR3 UNet + posterior update for one
+// (config, batch), owns device buffers / packed weights / TMA descriptors, captures the step as a CUDA graph and exposes
+// the C ABI declared in include/sr3_b200.h.  Reference call sites are cited in the header next to each entry point.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/sr3_b200.h"
+#include "aux_kernels.cuh"
+
+using namespace sr3;
+typedef __nv_bfloat16 bf16;
+
+namespace {
+
+thread_local std::string g_err;
+
+std::string fmt(const char* f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof(buf), f, ap);
+    va_end(ap);
+    return std::string(buf);
+}
+#define CK(expr)                                                                                                  \
+    do {                                                                                                          \
+        cudaError_t e_ = (expr);                                                                                  \
+        if (e_ != cudaSuccess) throw std::runtime_error(fmt("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_))); \
+    } while (0)
+#define REQUIRE(cond, ...)                                                 \
+    do {                                                                   \
+        if (!(cond)) throw std::runtime_error(fmt(__VA_ARGS__));           \
+    } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    REQUIRE(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available from the driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+CUtensorMap encode_map(int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+    CUtensorMap m;
+    cuuint64_t gd[5], gs[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
+    for (int i = 0; i < rank; ++i) REQUIRE(box[i] >= 1 && box[i] <= 256 && box[i] <= dims[i], "TMA box %u exceeds dim %llu (axis %d)", box[i], (unsigned long long)dims[i], i);
+    REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base not 16B aligned");
+    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return m;
+}
+
+// 5-D source view of an A operand: dims (C', W', P, H', Bn), byte strides of dims 1..4
+struct ASrc {
+    const void* ptr = nullptr;
+    int C = 0, W = 1, P = 1, H = 1, Bn = 1;
+    long long sW = 0, sP = 0, sH = 0, sB = 0;
+};
+ASrc nhwc_src(const void* ptr, int Bn, int H, int W, int C) {
+    ASrc a; a.ptr = ptr; a.C = C; a.W = W; a.P = 1; a.H = H; a.Bn = Bn;
+    a.sW = 2LL * C; a.sP = 2LL * W * C; a.sH = 2LL * W * C; a.sB = 2LL * H * W * C;
+    return a;
+}
+// stride-2 view of an NHWC tensor: (2C, W/2, 2, H/2, B)
+ASrc nhwc_stride2_src(const void* ptr, int Bn, int H, int W, int C) {
+    ASrc a; a.ptr = ptr; a.C = 2 * C; a.W = W / 2; a.P = 2; a.H = H / 2; a.Bn = Bn;
+    a.sW = 4LL * C; a.sP = 2LL * W * C; a.sH = 4LL * W * C; a.sB = 2LL * H * W * C;
+    return a;
+}
+// batched row-major matrices [nb][rows][K] (row stride ld elements)
+ASrc matrix_src(const void* ptr, int nb, int rows, int K, long long ld, long long batch_stride_elems) {
+    ASrc a; a.ptr = ptr; a.C = K; a.W = rows; a.P = 1; a.H = 1; a.Bn = nb;
+    a.sW = 2LL * ld; a.sP = 2LL * ld * rows; a.sH = 2LL * ld * rows; a.sB = 2LL * batch_stride_elems;
+    if (nb == 1) a.sB = a.sH;
+    return a;
+}
+
+struct KSlab { int a_sel, a_chan, dw, dh, p, b_col; };
+
+struct GemmDesc {
+    ASrc a[2];
+    int n_a = 1;
+    const void* b_ptr = nullptr;
+    long long b_rows = 0; int b_K = 0;            // B matrix [b_rows][b_K] bf16 row-major
+    std::vector<KSlab> slabs;
+    int block_n = 128;
+    int w_box = 16, h_box = 8, b_box = 1;
+    int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
+    int a_zstep = 0, b_zrows = 0;
+    // epilogue
+    int mode = 0, OW = 0, OH = 1, OB = 1, n_valid = 0;
+    float scale = 1.f;
+    const float* bias = nullptr; const float* bias2 = nullptr; int bias2_stride = 0;
+    const float* resid = nullptr; OutSpec rs{};
+    float* out_f32 = nullptr; OutSpec os{};
+    bf16* out_bf16 = nullptr; OutSpec hs{};
+    float* stats = nullptr; int stats_C = 0, stats_coff = 0;
+    const StepCtl* ctl = nullptr; PostParams post{};
+};
+
+OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
+    OutSpec s; s.sZ = 0; s.sB = 1LL * H * W * C; s.sH = 1LL * W * C; s.sW = C; s.off = off; return s;
+}
+
+int pick_stages(int block_n, int num_k) {
+    int s = block_n >= 256 ? 4 : (block_n == 128 ? 3 : 4);
+    if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
+    if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
+    if (s > num_k) s = num_k;
+    if (s < 1) s = 1;
+    return s;
+}
+
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
+template <int BN>
+void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
+    gemm_tile_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(p);
+    CK(cudaGetLastError());
+}
+void init_gemm_attrs() {
+    static bool done = false;
+    if (done) return;
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    done = true;
+}
+
+struct DevAllocs {
+    std::vector<void*> ptrs;
+    long long bytes = 0;
+    void* alloc(size_t n, bool zero = true) {
+        void* p = nullptr;
+        if (n == 0) n = 16;
+        CK(cudaMalloc(&p, n));
+        if (zero) CK(cudaMemset(p, 0, n));
+        ptrs.push_back(p);
+        bytes += (long long)n;
+        return p;
+    }
+    ~DevAllocs() { for (void* p : ptrs) cudaFree(p); }
+};
+
+typedef std::function<void(cudaStream_t)> Op;
+
+// Turns a GemmDesc into a launchable op (encodes the TMA maps, uploads the K-slab table).
+Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
+    REQUIRE(d.w_box * d.h_box * d.b_box == 128, "tile box must cover 128 rows");
+    REQUIRE(!d.slabs.empty(), "gemm without K slabs");
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    for (int i = 0; i < 2; ++i) {
+        const ASrc& a = d.a[i < d.n_a ? i : 0];
+        REQUIRE(a.C % 64 == 0, "A channels (%d) must be a multiple of 64", a.C);
+        const uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.P, (uint64_t)a.H, (uint64_t)a.Bn};
+        const uint64_t str[4] = {(uint64_t)a.sW, (uint64_t)a.sP, (uint64_t)a.sH, (uint64_t)a.sB};
+        const uint32_t box[5] = {64u, (uint32_t)d.w_box, 1u, (uint32_t)d.h_box, (uint32_t)d.b_box};
+        p.a_map[i] = encode_map(5, a.ptr, dims, str, box);
+    }
+    {
+        REQUIRE(d.b_K % 64 == 0, "B K extent must be a multiple of 64");
+        const uint64_t dims[2] = {(uint64_t)d.b_K, (uint64_t)d.b_rows};
+        const uint64_t str[1] = {2ull * d.b_K};
+        const uint32_t box[2] = {64u, (uint32_t)d.block_n};
+        REQUIRE(d.b_rows >= d.block_n, "B rows %lld < block_n %d", d.b_rows, d.block_n);
+        p.b_map = encode_map(2, d.b_ptr, dims, str, box);
+    }
+    std::vector<int4> tab(d.slabs.size());
+    for (size_t i = 0; i < d.slabs.size(); ++i) {
+        const KSlab& s = d.slabs[i];
+        REQUIRE(s.a_sel < d.n_a, "slab refers to missing A source");
+        tab[i] = make_int4(s.a_sel, s.a_chan, (s.dw & 0xff) | ((s.dh & 0xff) << 8) | ((s.p & 0xff) << 16), s.b_col);
+    }
+    int4* dtab = static_cast<int4*>(mem.alloc(tab.size() * sizeof(int4), false));
+    CK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    p.ktab = dtab; p.num_k = (int)tab.size();
+    p.tiles_w = d.tiles_w; p.tiles_h = d.tiles_h; p.tiles_b = d.tiles_b;
+    p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
+    p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
+    p.stages = pick_stages(d.block_n, p.num_k);
+    p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
+    p.bias = d.bias; p.bias2 = d.bias2; p.bias2_stride = d.bias2_stride;
+    p.resid = d.resid; p.rs = d.rs; p.out_f32 = d.out_f32; p.os = d.os; p.out_bf16 = d.out_bf16; p.hs = d.hs;
+    p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
+    if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
+    const dim3 grid(d.tiles_w * d.tiles_h * d.tiles_b, d.n_tiles, d.nz);
+    const int bn = d.block_n;
+    while (gemm_smem_bytes(bn, p.stages) > SMEM_LIMIT && p.stages > 1) --p.stages;
+    const int smem = gemm_smem_bytes(bn, p.stages);
+    init_gemm_attrs();
+    REQUIRE(bn == 16 || bn == 64 || bn == 128 || bn == 256, "unsupported block_n %d", bn);
+    return [p, grid, bn, smem](cudaStream_t st) {
+        switch (bn) {
+            case 16: launch_gemm_bn<16>(p, grid, smem, st); break;
+            case 64: launch_gemm_bn<64>(p, grid, smem, st); break;
+            case 128: launch_gemm_bn<128>(p, grid, smem, st); break;
+            default: launch_gemm_bn<256>(p, grid, smem, st); break;
+        }
+    };
+}
+
+void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box) {
+    w_box = W < 16 ? W : 16;
+    h_box = 128 / w_box;
+    if (h_box > H) h_box = H;
+    b_box = 128 / (w_box * h_box);
+}
+
+int pick_block_n(int cout) {
+    if (const char* e = getenv("SR3_BLOCK_N")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) if (cout % v == 0) return v; }
+    if (cout % 128 == 0) return 128;
+    if (cout % 64 == 0) return 64;
+    return 16;
+}
+
+void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, int stride, int b_col0) {
+    if (ksize == 1) {
+        for (int c = 0; c < cin; c += 64) slabs.push_back({a_sel, c, 0, 0, 0, b_col0 + c});
+        return;
+    }
+    for (int r = 0; r < 3; ++r)
+        for (int s = 0; s < 3; ++s)
+            for (int c = 0; c < cin; c += 64) {
+                KSlab k; k.a_sel = a_sel; k.b_col = b_col0 + (r * 3 + s) * cin + c;
+                if (stride == 1) { k.dh = r - 1; k.dw = s - 1; k.p = 0; k.a_chan = c; }
+                else {   // input row 2*oh + r - 1, column 2*ow + s - 1 in the (2C, W/2, 2, H/2, B) view
+                    k.dh = (r == 0) ? -1 : 0; k.p = (r == 1) ? 0 : 1;
+                    k.dw = (s == 0) ? -1 : 0; k.a_chan = ((s == 1) ? 0 : cin) + c;
+                }
+                slabs.push_back(k);
+            }
+}
+
+// ------------------------------------------------------------------------------------------------ engine
+struct Act {
+    float* p = nullptr; float* stats = nullptr;
+    int C = 0, H = 0, W = 0;
+};
+
+struct ParamEntry {
+    std::string name;
+    std::vector<int64_t> shape;
+    int64_t numel = 0;
+    std::function<void(const float*, cudaStream_t)> load;
+    bool loaded = false;
+};
+
+struct LayerSpec { std::string name; int kind; int cin, cout; bool attn; int res; };   // kind: 0 conv, 1 res, 2 down, 3 up
+
+}  // namespace
+
+struct sr3_engine {
+    sr3_unet_config cfg{};
+    int B = 0, Bp = 0, dev = 0;
+    int H = 0, W = 0, inner = 0, cond_c = 0, in_C = 64;
+    DevAllocs mem;
+    std::vector<ParamEntry> params;
+    std::map<std::string, int> pindex;
+    std::vector<Op> ops, finalize_ops;
+    std::map<std::string, Act> taps;
+    std::map<std::string, size_t> role_max;
+    std::map<std::string, void*> role_ptr;
+    bool dry = true;
+
+    StepCtl* ctl_dev = nullptr;
+    StepCtl ctl{};
+    float* stats_arena = nullptr; size_t stats_cap = 0, stats_used = 0;
+    bf16* in_buf = nullptr;
+    float *x_state = nullptr, *eps_buf = nullptr, *mean_buf = nullptr, *noise_buf = nullptr, *nl_buf = nullptr, *io_a = nullptr, *io_b = nullptr;
+    float *nl_table = nullptr, *post_tab = nullptr;
+    int T = 0, T_cap = 0;
+    std::vector<float> logvar_host;
+    float *tau = nullptr, *film = nullptr, *film_w = nullptr, *film_b = nullptr, *film_cb = nullptr;
+    float *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr, *mlp_b2 = nullptr;
+    int F = 0;
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t cap_stream = nullptr;
+    bool use_graph = true;
+    uint64_t seed = 0, first_index = 0;
+    bool have_cond = false;
+
+    ~sr3_engine() {
+        if (graph) cudaGraphExecDestroy(graph);
+        if (cap_stream) cudaStreamDestroy(cap_stream);
+    }
+
+    // ---- buffers shared between layers of the same role (stream order makes reuse safe)
+    void* role(const std::string& r, size_t bytes) {
+        if (dry) { size_t& m = role_max[r]; if (bytes > m) m = bytes; return reinterpret_cast<void*>(0x1000); }
+        REQUIRE(role_ptr.count(r) && role_max[r] >= bytes, "role buffer %s too small", r.c_str());
+        return role_ptr[r];
+    }
+    float* new_stats(int C) {
+        const size_t n = (size_t)Bp * C * 2;
+        if (dry) { stats_used += n; return nullptr; }
+        REQUIRE(stats_used + n <= stats_cap, "stats arena overflow");
+        float* p = stats_arena + stats_used;
+        stats_used += n;
+        return p;
+    }
+    Act new_act(int C, int Hh, int Ww, const std::string& tap_name = "") {
+        Act a; a.C = C; a.H = Hh; a.W = Ww;
+        a.stats = new_stats(C);
+        if (!dry) {
+            a.p = static_cast<float*>(mem.alloc((size_t)Bp * Hh * Ww * C * sizeof(float)));
+            if (!tap_name.empty()) taps[tap_name] = a;
+        }
+        return a;
+    }
+    void add_param(const std::string& name, std::vector<int64_t> shape, std::function<void(const float*, cudaStream_t)> load) {
+        if (dry) return;
+        ParamEntry e; e.name = name; e.shape = shape; e.numel = 1;
+        for (auto s : shape) e.numel *= s;
+        e.load = std::move(load);
+        pindex[name] = (int)params.size();
+        params.push_back(std::move(e));
+    }
+    float* f32_param(const std::string& name, std::vector<int64_t> shape) {
+        if (dry) return nullptr;
+        int64_t n = 1; for (auto s : shape) n *= s;
+        float* dst = static_cast<float*>(mem.alloc(n * sizeof(float)));
+        add_param(name, shape, [dst, n](const float* src, cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
+        return dst;
+    }
+    // f32 parameter stored into a slice of a bigger array
+    void f32_param_into(const std::string& name, std::vector<int64_t> shape, float* dst) {
+        if (dry) return;
+        int64_t n = 1; for (auto s : shape) n *= s;
+        add_param(name, shape, [dst, n](const float* src, cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
+    }
+    // conv weight packed into rows [0,Cout) of a [rows_pad][ktot] bf16 matrix at column k_off
+    void conv_weight_param(const std::string& name, bf16* dst, int Cout, int Cin, int k, int ktot, int k_off, int cin_pad) {
+        if (dry) return;
+        add_param(name, {Cout, Cin, k, k}, [=](const float* src, cudaStream_t st) {
+            const long long total = 1LL * Cout * Cin * k * k;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(src, dst, Cout, Cin, k, k, ktot, k_off, cin_pad);
+            CK(cudaGetLastError());
+        });
+    }
+    bf16* new_weight(int rows, int ktot, int block_n) {
+        if (dry) return nullptr;
+        const int rows_pad = ((rows + block_n - 1) / block_n) * block_n;
+        return static_cast<bf16*>(mem.alloc((size_t)rows_pad * ktot * sizeof(bf16)));
+    }
+    void push(Op op) { if (!dry) ops.push_back(std::move(op)); }
+
+    // ---- layer builders -------------------------------------------------------------------------
+    void add_prep(const Act& s0, const Act* s1, const float* gamma, const float* beta, int groups, bool silu, bf16* out_a, bf16* out_raw) {
+        if (dry) return;
+        PrepParams p{};
+        p.src0 = s0.p; p.st0 = s0.stats; p.C0 = s0.C;
+        p.src1 = s1 ? s1->p : nullptr; p.st1 = s1 ? s1->stats : nullptr; p.C1 = s1 ? s1->C : 0;
+        p.gamma = gamma; p.beta = beta; p.groups = groups; p.HW = s0.H * s0.W; p.silu = silu ? 1 : 0; p.eps = 1e-5f;
+        p.out_a = out_a; p.out_raw = out_raw;
+        const int C = p.C0 + p.C1;
+        REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
+        int ppb = 16384 / C; if (ppb < 8) ppb = 8; if (ppb > p.HW) ppb = p.HW;
+        p.pix_per_block = ppb;
+        const dim3 grid((p.HW + ppb - 1) / ppb, B);
+        const int smem = (2 * C + 2 * groups) * sizeof(float);
+        push([p, grid, smem](cudaStream_t st) { prep_kernel<<<grid, 256, smem, st>>>(p); CK(cudaGetLastError()); });
+    }
+    void add_cast(const Act& s, bf16* dst, int up) {
+        if (dry) return;
+        const long long total = 1LL * B * s.H * up * s.W * up * (s.C / 4);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        const float* src = s.p; const int Bn = B, Hh = s.H, Ww = s.W, C = s.C;
+        push([=](cudaStream_t st) { cast_kernel<<<blocks, 256, 0, st>>>(src, dst, Bn, Hh, Ww, C, up); CK(cudaGetLastError()); });
+    }
+
+    // generic image conv: A sources already bf16; out fp32 NHWC (+stats)
+    struct ConvArgs {
+        ASrc a[2]; int n_a = 1;
+        std::vector<KSlab> slabs;
+        const bf16* w = nullptr; int ktot = 0; int cout = 0;
+        int OH = 0, OW = 0;
+        const float* bias = nullptr; const float* bias2 = nullptr; int bias2_stride = 0;
+        const float* resid = nullptr;
+        Act out;
+    };
+    void add_conv(const ConvArgs& c) {
+        if (dry) return;
+        GemmDesc d;
+        d.n_a = c.n_a; d.a[0] = c.a[0]; d.a[1] = c.a[1];
+        d.slabs = c.slabs;
+        d.block_n = pick_block_n(c.cout);
+        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + d.block_n - 1) / d.block_n) * d.block_n;
+        pick_image_box(c.OW, c.OH, d.w_box, d.h_box, d.b_box);
+        d.tiles_w = c.OW / d.w_box; d.tiles_h = c.OH / d.h_box; d.tiles_b = Bp / d.b_box;
+        d.n_tiles = (int)(d.b_rows / d.block_n); d.nz = 1;
+        d.OW = c.OW; d.OH = c.OH; d.OB = B; d.n_valid = c.cout;
+        d.bias = c.bias; d.bias2 = c.bias2; d.bias2_stride = c.bias2_stride;
+        d.resid = c.resid; d.rs = nhwc_out(c.OH, c.OW, c.cout);
+        d.out_f32 = c.out.p; d.os = nhwc_out(c.OH, c.OW, c.cout);
+        d.stats = c.out.stats; d.stats_C = c.cout; d.stats_coff = 0;
+        push(make_gemm_op(d, mem));
+    }
+
+    // ResnetBlock (+ optional SelfAttention): reference unet.py:94-158
+    Act add_res_block(const LayerSpec& L, const Act& x, const Act* skip, int& film_off) {
+        const int cin = x.C + (skip ? skip->C : 0), cout = L.cout, Hh = x.H, Ww = x.W, G = cfg.norm_groups;
+        REQUIRE(cin == L.cin, "%s: cin mismatch %d vs %d", L.name.c_str(), cin, L.cin);
+        const std::string p = L.name + ".res_block";
+        const bool has_res = cin != cout;
+        // parameters in the reference's registration order
+        const int foff = film_off; film_off += cout;
+        f32_param_into(p + ".noise_func.noise_func.0.weight", {cout, inner}, dry ? nullptr : film_w + (size_t)foff * inner);
+        f32_param_into(p + ".noise_func.noise_func.0.bias", {cout}, dry ? nullptr : film_b + foff);
+        float* g1 = f32_param(p + ".block1.block.0.weight", {cin});
+        float* b1 = f32_param(p + ".block1.block.0.bias", {cin});
+        bf16* w1 = new_weight(cout, 9 * cin, pick_block_n(cout));
+        conv_weight_param(p + ".block1.block.3.weight", w1, cout, cin, 3, 9 * cin, 0, cin);
+        f32_param_into(p + ".block1.block.3.bias", {cout}, dry ? nullptr : film_cb + foff);
+        float* g2 = f32_param(p + ".block2.block.0.weight", {cout});
+        float* b2 = f32_param(p + ".block2.block.0.bias", {cout});
+        const int k2 = 9 * cout + (has_res ? cin : 0);
+        bf16* w2 = new_weight(cout, k2, pick_block_n(cout));
+        conv_weight_param(p + ".block2.block.3.weight", w2, cout, cout, 3, k2, 0, cout);
+        float* cb2 = f32_param(p + ".block2.block.3.bias", {cout});
+        float* bias_total = cb2;
+        if (has_res) {
+            conv_weight_param(p + ".res_conv.weight", w2, cout, cin, 1, k2, 9 * cout, cin);
+            float* cbr = f32_param(p + ".res_conv.bias", {cout});
+            if (!dry) {
+                bias_total = static_cast<float*>(mem.alloc(cout * sizeof(float)));
+                float* bt = bias_total;
+                finalize_ops.push_back([=](cudaStream_t st) { add_vec_kernel<<<(cout + 255) / 256, 256, 0, st>>>(cb2, cbr, bt, cout); CK(cudaGetLastError()); });
+            }
+        }
+        // scratch
+        bf16* a1 = static_cast<bf16*>(role("a1", (size_t)Bp * Hh * Ww * cin * 2));
+        bf16* raw = has_res ? static_cast<bf16*>(role("raw", (size_t)Bp * Hh * Ww * cin * 2)) : nullptr;
+        bf16* a2 = static_cast<bf16*>(role("a2", (size_t)Bp * Hh * Ww * cout * 2));
+        Act h; h.C = cout; h.H = Hh; h.W = Ww; h.stats = new_stats(cout);
+        h.p = static_cast<float*>(role("h", (size_t)Bp * Hh * Ww * cout * 4));
+        Act y = new_act(cout, Hh, Ww, L.attn ? "" : L.name);
+
+        add_prep(x, skip, g1, b1, G, true, a1, raw);
+        {
+            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(a1, Bp, Hh, Ww, cin);
+            add_conv_slabs(c.slabs, 0, cin, 3, 1, 0);
+            c.w = w1; c.ktot = 9 * cin; c.cout = cout; c.OH = Hh; c.OW = Ww;
+            c.bias2 = dry ? nullptr : film + foff; c.bias2_stride = F;
+            c.out = h;
+            add_conv(c);
+        }
+        add_prep(h, nullptr, g2, b2, G, true, a2, nullptr);
+        {
+            ConvArgs c; c.n_a = has_res ? 2 : 1; c.a[0] = nhwc_src(a2, Bp, Hh, Ww, cout);
+            add_conv_slabs(c.slabs, 0, cout, 3, 1, 0);
+            if (has_res) { c.a[1] = nhwc_src(raw, Bp, Hh, Ww, cin); add_conv_slabs(c.slabs, 1, cin, 1, 1, 9 * cout); }
+            c.w = w2; c.ktot = k2; c.cout = cout; c.OH = Hh; c.OW = Ww;
+            c.bias = bias_total; c.resid = has_res ? nullptr : x.p;
+            c.out = y;
+            add_conv(c);
+        }
+        if (!L.attn) return y;
+        return add_attention(L, y);
+    }
+
+    // SelfAttention (reference unet.py:113-142): GN -> qkv 1x1 (no bias) -> softmax(q k^T / sqrt(C)) v -> out 1x1 + bias + x
+    Act add_attention(const LayerSpec& L, const Act& x) {
+        const int C = x.C, Hh = x.H, Ww = x.W, HW = Hh * Ww, G = cfg.norm_groups;
+        const std::string p = L.name + ".attn";
+        const int Lt = HW >= 128 ? HW : 128;            // tokens per attention batch (two 8x8 images share one)
+        const int per = Lt / HW;                         // images per attention batch
+        REQUIRE(Lt % 128 == 0 && (Bp % per) == 0, "attention geometry HW=%d", HW);
+        const int nz = Bp / per;
+        float* gn_w = f32_param(p + ".norm.weight", {C});
+        float* gn_b = f32_param(p + ".norm.bias", {C});
+        bf16* wqkv = new_weight(3 * C, C, 128);
+        conv_weight_param(p + ".qkv.weight", wqkv, 3 * C, C, 1, C, 0, C);
+        bf16* wout = new_weight(C, C, 128);
+        conv_weight_param(p + ".out.weight", wout, C, C, 1, C, 0, C);
+        float* bout = f32_param(p + ".out.bias", {C});
+        bf16* n = static_cast<bf16*>(role("a1", (size_t)Bp * HW * C * 2));
+        bf16* qk = static_cast<bf16*>(role("qk", (size_t)Bp * HW * 2 * C * 2));
+        bf16* vT = static_cast<bf16*>(role("vT", (size_t)nz * C * Lt * 2));
+        float* S = static_cast<float*>(role("S", (size_t)nz * Lt * Lt * 4));
+        bf16* P = static_cast<bf16*>(role("P", (size_t)nz * Lt * Lt * 2));
+        bf16* O = static_cast<bf16*>(role("O", (size_t)Bp * HW * C * 2));
+        Act y = new_act(C, Hh, Ww, L.name);
+        add_prep(x, nullptr, gn_w, gn_b, G, false, n, nullptr);
+        if (dry) return y;
+        {   // q,k = Wqk n : [Bp*HW tokens] x [2C]
+            GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C);
+            add_conv_slabs(d.slabs, 0, C, 1, 1, 0);
+            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = 2 * C;
+            pick_image_box(Ww, Hh, d.w_box, d.h_box, d.b_box);
+            d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 2 * C / 128;
+            d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = 2 * C;
+            d.out_bf16 = qk; d.hs = nhwc_out(Hh, Ww, 2 * C);
+            push(make_gemm_op(d, mem));
+        }
+        {   // vT[z][d][token] = Wv[d,:] . n[token,:]  (weights are the A operand, tokens the B operand)
+            GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(wqkv + (size_t)2 * C * C, 1, C, C, C, 0);
+            for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
+            d.block_n = 128; d.b_ptr = n; d.b_K = C; d.b_rows = (long long)Bp * HW;
+            d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = C / 128; d.tiles_h = 1; d.tiles_b = 1;
+            d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 0; d.b_zrows = Lt;
+            d.OW = C; d.OH = 1; d.OB = 1; d.n_valid = Lt;
+            d.out_bf16 = vT; d.hs = OutSpec{(long long)C * Lt, 0, 0, Lt, 0};
+            push(make_gemm_op(d, mem));
+        }
+        {   // S[z] = q k^T / sqrt(C)
+            GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C, 2 * C, (long long)Lt * 2 * C);
+            for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, C + c});
+            d.block_n = 128; d.b_ptr = qk; d.b_K = 2 * C; d.b_rows = (long long)Bp * HW;
+            d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
+            d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = Lt;
+            d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = Lt; d.scale = 1.0f / sqrtf((float)C);
+            d.out_f32 = S; d.os = OutSpec{0, (long long)Lt * Lt, 0, Lt, 0};
+            push(make_gemm_op(d, mem));
+        }
+        {
+            const long long rows = (long long)nz * Lt;
+            const int blocks = (int)((rows + 7) / 8);
+            push([=](cudaStream_t st) { softmax_kernel<<<blocks, 256, 0, st>>>(S, P, rows, Lt, HW); CK(cudaGetLastError()); });
+        }
+        {   // O[z] = P v : rows = queries, N = head dim, K = keys
+            GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
+            for (int c = 0; c < Lt; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
+            d.block_n = 128; d.b_ptr = vT; d.b_K = Lt; d.b_rows = (long long)nz * C;
+            d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
+            d.n_tiles = C / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = C;
+            d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = C;
+            d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C, 0, C, 0};
+            push(make_gemm_op(d, mem));
+        }
+        {   // out projection + bias + residual (un-normalised input)
+            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(O, Bp, Hh, Ww, C);
+            add_conv_slabs(c.slabs, 0, C, 1, 1, 0);
+            c.w = wout; c.ktot = C; c.cout = C; c.OH = Hh; c.OW = Ww; c.bias = bout; c.resid = x.p; c.out = y;
+            add_conv(c);
+        }
+        return y;
+    }
+
+    void build_plan() {
+        // topology: reference unet.py:186-231
+        std::vector<LayerSpec> downs, mid, ups;
+        std::vector<int> feat;
+        int pre = inner, res = cfg.image_size;
+        feat.push_back(pre);
+        downs.push_back({"downs.0", 0, cfg.in_channel, inner, false, res});
+        for (int ind = 0; ind < cfg.n_mults; ++ind) {
+            const bool last = ind == cfg.n_mults - 1;
+            bool use_attn = false;
+            for (int i = 0; i < cfg.n_attn_res; ++i) use_attn |= (cfg.attn_res[i] == res);
+            const int ch = inner * cfg.channel_mults[ind];
+            for (int r = 0; r < cfg.res_blocks; ++r) {
+                downs.push_back({"downs." + std::to_string(downs.size()), 1, pre, ch, use_attn, res});
+                feat.push_back(ch); pre = ch;
+            }
+            if (!last) { downs.push_back({"downs." + std::to_string(downs.size()), 2, pre, pre, false, res}); feat.push_back(pre); res /= 2; }
+        }
+        mid.push_back({"mid.0", 1, pre, pre, true, res});
+        mid.push_back({"mid.1", 1, pre, pre, false, res});
+        for (int ind = cfg.n_mults - 1; ind >= 0; --ind) {
+            const bool last = ind < 1;
+            bool use_attn = false;
+            for (int i = 0; i < cfg.n_attn_res; ++i) use_attn |= (cfg.attn_res[i] == res);
+            const int ch = inner * cfg.channel_mults[ind];
+            for (int r = 0; r < cfg.res_blocks + 1; ++r) {
+                ups.push_back({"ups." + std::to_string(ups.size()), 1, pre + feat.back(), ch, use_attn, res});
+                feat.pop_back(); pre = ch;
+            }
+            if (!last) { ups.push_back({"ups." + std::to_string(ups.size()), 3, pre, pre, false, res}); res *= 2; }
+        }
+        int F_total = 0;
+        for (auto* v : {&downs, &mid, &ups}) for (auto& L : *v) if (L.kind == 1) F_total += L.cout;
+        F = F_total;
+        int min_res = cfg.image_size;
+        for (int i = 1; i < cfg.n_mults; ++i) min_res /= 2;
+        REQUIRE(min_res >= 8, "lowest UNet resolution %d < 8 is not supported", min_res);
+
+        if (!dry) {
+            mlp_w1 = f32_param("noise_level_mlp.1.weight", {4 * inner, inner});
+            mlp_b1 = f32_param("noise_level_mlp.1.bias", {4 * inner});
+            mlp_w2 = f32_param("noise_level_mlp.3.weight", {inner, 4 * inner});
+            mlp_b2 = f32_param("noise_level_mlp.3.bias", {inner});
+            film_w = static_cast<float*>(mem.alloc((size_t)F * inner * 4));
+            film_b = static_cast<float*>(mem.alloc((size_t)F * 4));
+            film_cb = static_cast<float*>(mem.alloc((size_t)F * 4));
+            film = static_cast<float*>(mem.alloc((size_t)Bp * F * 4));
+            tau = static_cast<float*>(mem.alloc((size_t)Bp * inner * 4));
+            // step prologue
+            float4* sa = reinterpret_cast<float4*>(stats_arena);
+            const long long n4 = (long long)(stats_cap / 4);
+            StepCtl* c = ctl_dev;
+            push([=](cudaStream_t st) { step_begin_kernel<<<(int)std::min<long long>((n4 + 255) / 256, 592), 256, 0, st>>>(sa, n4, c); CK(cudaGetLastError()); });
+            EmbedParams ep{}; ep.ctl = ctl_dev; ep.nl_table = nl_table; ep.nl_buf = nl_buf; ep.w1 = mlp_w1; ep.b1 = mlp_b1; ep.w2 = mlp_w2; ep.b2 = mlp_b2;
+            ep.tau = tau; ep.inner = inner;
+            const int Bn = B; const int esm = 5 * inner * 4;
+            push([=](cudaStream_t st) { embed_kernel<<<Bn, 256, esm, st>>>(ep); CK(cudaGetLastError()); });
+            float *fw = film_w, *fb = film_b, *fc = film_cb, *ta = tau, *fi = film; const int Fn = F, inn = inner;
+            push([=](cudaStream_t st) { film_kernel<<<dim3((Fn + 255) / 256, Bn), 256, 0, st>>>(fw, fb, fc, ta, fi, Fn, inn); CK(cudaGetLastError()); });
+        }
+
+        int film_off = 0;
+        std::vector<Act> feats;
+        Act x;
+        for (auto& L : downs) {
+            if (L.kind == 0) {          // first conv on the (zero-padded to 64 ch) input buffer
+                bf16* w = new_weight(inner, 9 * in_C, pick_block_n(inner));
+                conv_weight_param(L.name + ".weight", w, inner, cfg.in_channel, 3, 9 * in_C, 0, in_C);
+                float* b = f32_param(L.name + ".bias", {inner});
+                x = new_act(inner, H, W, L.name);
+                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(in_buf, Bp, H, W, in_C);
+                add_conv_slabs(c.slabs, 0, in_C, 3, 1, 0);
+                c.w = w; c.ktot = 9 * in_C; c.cout = inner; c.OH = H; c.OW = W; c.bias = b; c.out = x;
+                add_conv(c);
+            } else if (L.kind == 1) {
+                x = add_res_block(L, x, nullptr, film_off);
+            } else {                    // Downsample: conv3x3 stride 2 on the raw stream (unet.py:68-74)
+                const int C = x.C;
+                bf16* w = new_weight(C, 9 * C, pick_block_n(C));
+                conv_weight_param(L.name + ".conv.weight", w, C, C, 3, 9 * C, 0, C);
+                float* b = f32_param(L.name + ".conv.bias", {C});
+                bf16* raw = static_cast<bf16*>(role("raw", (size_t)Bp * x.H * x.W * C * 2));
+                add_cast(x, raw, 1);
+                Act y = new_act(C, x.H / 2, x.W / 2, L.name);
+                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_stride2_src(raw, Bp, x.H, x.W, C);
+                add_conv_slabs(c.slabs, 0, C, 3, 2, 0);
+                c.w = w; c.ktot = 9 * C; c.cout = C; c.OH = y.H; c.OW = y.W; c.bias = b; c.out = y;
+                add_conv(c);
+                x = y;
+            }
+            feats.push_back(x);
+        }
+        for (auto& L : mid) x = add_res_block(L, x, nullptr, film_off);
+        for (auto& L : ups) {
+            if (L.kind == 1) {
+                Act skip = feats.back(); feats.pop_back();
+                x = add_res_block(L, x, &skip, film_off);
+            } else {                    // Upsample: nearest 2x then conv3x3 (unet.py:58-65)
+                const int C = x.C;
+                bf16* w = new_weight(C, 9 * C, pick_block_n(C));
+                conv_weight_param(L.name + ".conv.weight", w, C, C, 3, 9 * C, 0, C);
+                float* b = f32_param(L.name + ".conv.bias", {C});
+                bf16* upb = static_cast<bf16*>(role("raw", (size_t)Bp * x.H * 2 * x.W * 2 * C * 2));
+                add_cast(x, upb, 2);
+                Act y = new_act(C, x.H * 2, x.W * 2, L.name);
+                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(upb, Bp, y.H, y.W, C);
+                add_conv_slabs(c.slabs, 0, C, 3, 1, 0);
+                c.w = w; c.ktot = 9 * C; c.cout = C; c.OH = y.H; c.OW = y.W; c.bias = b; c.out = y;
+                add_conv(c);
+                x = y;
+            }
+        }
+        REQUIRE(film_off == F, "film bookkeeping");
+        {   // final Block (GN -> SiLU -> conv 64 -> out_channel) with the eps / posterior epilogue
+            const int C = x.C, co = cfg.out_channel;
+            REQUIRE(co <= 4 && co == cfg.channels, "out_channel must equal diffusion channels (<=4)");
+            float* g = f32_param("final_conv.block.0.weight", {C});
+            float* be = f32_param("final_conv.block.0.bias", {C});
+            bf16* w = new_weight(co, 9 * C, 16);
+            conv_weight_param("final_conv.block.3.weight", w, co, C, 3, 9 * C, 0, C);
+            float* b = f32_param("final_conv.block.3.bias", {co});
+            bf16* a = static_cast<bf16*>(role("a1", (size_t)Bp * H * W * C * 2));
+            add_prep(x, nullptr, g, be, cfg.norm_groups, true, a, nullptr);
+            if (!dry) {
+                GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C);
+                add_conv_slabs(d.slabs, 0, C, 3, 1, 0);
+                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 16;
+                pick_image_box(W, H, d.w_box, d.h_box, d.b_box);
+                d.tiles_w = W / d.w_box; d.tiles_h = H / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 1;
+                d.mode = 1; d.OW = W; d.OH = H; d.OB = B; d.n_valid = co; d.bias = b; d.ctl = ctl_dev;
+                d.post.tab = post_tab; d.post.T = T_cap; d.post.H = H; d.post.W = W; d.post.C = co;
+                d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
+                d.post.in_buf = in_buf; d.post.in_C = in_C; d.post.in_coff = cond_c;
+                push(make_gemm_op(d, mem));
+            }
+        }
+    }
+
+    void init(const sr3_unet_config& c, int batch, int device) {
+        cfg = c; B = batch; dev = device;
+        CK(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        REQUIRE(prop.major == 10, "sr3_b200 needs an sm_100 class GPU (found sm_%d%d); there is no fallback path", prop.major, prop.minor);
+        REQUIRE(B >= 1, "batch must be >= 1");
+        REQUIRE(cfg.inner_channel % 64 == 0, "inner_channel must be a multiple of 64 (got %d)", cfg.inner_channel);
+        REQUIRE(cfg.in_channel <= 64, "in_channel must be <= 64");
+        REQUIRE(cfg.n_mults >= 1 && cfg.n_mults <= SR3_MAX_LEVELS, "bad n_mults");
+        for (int i = 0; i < cfg.n_mults; ++i) REQUIRE((cfg.inner_channel * cfg.channel_mults[i]) % (2 * cfg.norm_groups) == 0 || (cfg.inner_channel * cfg.channel_mults[i]) % cfg.norm_groups == 0, "norm_groups must divide the channel counts");
+        inner = cfg.inner_channel; H = W = cfg.image_size;
+        cond_c = cfg.conditional ? cfg.in_channel - cfg.channels : 0;
+        Bp = (B + 1) & ~1;                         // 8x8 levels tile two images per CTA
+        use_graph = getenv("SR3_NO_GRAPH") == nullptr;
+        T_cap = 4096;
+        // pass 1: sizes
+        dry = true; stats_used = 0;
+        build_plan();
+        // allocate
+        stats_cap = (stats_used + 3) & ~size_t(3);
+        stats_arena = static_cast<float*>(mem.alloc(stats_cap * sizeof(float)));
+        for (auto& kv : role_max) role_ptr[kv.first] = mem.alloc(kv.second);
+        ctl_dev = static_cast<StepCtl*>(mem.alloc(sizeof(StepCtl)));
+        in_buf = static_cast<bf16*>(mem.alloc((size_t)Bp * H * W * in_C * 2));
+        const size_t img = (size_t)Bp * cfg.channels * H * W * 4;
+        x_state = static_cast<float*>(mem.alloc(img)); eps_buf = static_cast<float*>(mem.alloc(img));
+        mean_buf = static_cast<float*>(mem.alloc(img)); noise_buf = static_cast<float*>(mem.alloc(img));
+        io_a = static_cast<float*>(mem.alloc(img)); io_b = static_cast<float*>(mem.alloc(img));
+        nl_buf = static_cast<float*>(mem.alloc(Bp * 4));
+        nl_table = static_cast<float*>(mem.alloc((T_cap + 1) * 4));
+        post_tab = static_cast<float*>(mem.alloc((size_t)5 * T_cap * 4));
+        // pass 2: real plan
+        dry = false; stats_used = 0;
+        build_plan();
+        CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+        CK(cudaDeviceSynchronize());
+    }
+
+    void run_step(cudaStream_t st) {
+        if (!use_graph) { for (auto& op : ops) op(st); return; }
+        if (!graph) {
+            cudaGraph_t g;
+            CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+            for (auto& op : ops) op(cap_stream);
+            CK(cudaStreamEndCapture(cap_stream, &g));
+            CK(cudaGraphInstantiate(&graph, g, 0));
+            CK(cudaGraphDestroy(g));
+        }
+        CK(cudaGraphLaunch(graph, st));
+    }
+    void push_ctl(cudaStream_t st) { CK(cudaMemcpyAsync(ctl_dev, &ctl, sizeof(StepCtl), cudaMemcpyHostToDevice, st)); }
+    void load_nchw(const float* src, int C, int coff, float* copy, cudaStream_t st) {
+        const long long total = 1LL * B * C * H * W;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+        load_nchw_kernel<<<blocks, 256, 0, st>>>(src, B, C, H, W, in_buf, in_C, coff, copy);
+        CK(cudaGetLastError());
+    }
+    size_t img_bytes() const { return (size_t)B * cfg.channels * H * W * 4; }
+    void check_params() {
+        for (auto& p : params) REQUIRE(p.loaded, "parameter %s was never loaded", p.name.c_str());
+    }
+    void load_inputs(const float* x, const float* cond, cudaStream_t st) {
+        if (cfg.conditional) { REQUIRE(cond != nullptr, "condition_x is required by a conditional model"); load_nchw(cond, cond_c, 0, nullptr, st); }
+        else REQUIRE(cond == nullptr, "condition_x given to an unconditional model");
+        load_nchw(x, cfg.channels, cond_c, x_state, st);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------ C ABI
+#define API_BEGIN try {
+#define API_END                      \
+    }                                \
+    catch (const std::exception& e) { \
+        g_err = e.what();            \
+        return 1;                    \
+    }                                \
+    return 0;
+
+extern "C" {
+
+const char* sr3_last_error(void) { return g_err.c_str(); }
+int sr3_abi_version(void) { return 1; }
+
+int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out) {
+    API_BEGIN
+    REQUIRE(cfg && out, "null argument");
+    std::unique_ptr<sr3_engine> e(new sr3_engine());
+    e->init(*cfg, batch, device);
+    *out = e.release();
+    API_END
+}
+void sr3_engine_destroy(sr3_engine* e) { delete e; }
+
+int sr3_engine_num_params(const sr3_engine* e) { return e ? (int)e->params.size() : 0; }
+int sr3_engine_param_info(const sr3_engine* e, int index, char* name, int name_cap, int64_t shape[4], int* ndim) {
+    API_BEGIN
+    REQUIRE(e && index >= 0 && index < (int)e->params.size(), "bad param index");
+    const ParamEntry& p = e->params[index];
+    if (name && name_cap > 0) { strncpy(name, p.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    for (int i = 0; i < 4; ++i) shape[i] = i < (int)p.shape.size() ? p.shape[i] : 1;
+    if (ndim) *ndim = (int)p.shape.size();
+    API_END
+}
+int sr3_engine_load_param(sr3_engine* e, const char* name, const float* src, int64_t numel, void* stream) {
+    API_BEGIN
+    REQUIRE(e && name && src, "null argument");
+    auto it = e->pindex.find(name);
+    REQUIRE(it != e->pindex.end(), "unexpected key in state_dict: %s", name);
+    ParamEntry& p = e->params[it->second];
+    REQUIRE(p.numel == numel, "size mismatch for %s: expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
+    CK(cudaSetDevice(e->dev));
+    p.load(src, static_cast<cudaStream_t>(stream));
+    p.loaded = true;
+    API_END
+}
+int sr3_engine_finalize_params(sr3_engine* e, void* stream) {
+    API_BEGIN
+    REQUIRE(e, "null engine");
+    e->check_params();
+    for (auto& op : e->finalize_ops) op(static_cast<cudaStream_t>(stream));
+    API_END
+}
+
+int sr3_engine_set_schedule(sr3_engine* e, int T, const float* a, const float* b, const float* c1, const float* c2, const float* lv,
+                            const double* sqrt_ac_prev, void* stream) {
+    API_BEGIN
+    REQUIRE(e && a && b && c1 && c2 && lv && sqrt_ac_prev, "null argument");
+    REQUIRE(T >= 1 && T <= e->T_cap, "n_timestep %d out of range (max %d)", T, e->T_cap);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->T = T;
+    std::vector<float> tab((size_t)5 * e->T_cap, 0.f), nl(T + 1);
+    const float* srcs[5] = {a, b, c1, c2, lv};
+    for (int k = 0; k < 5; ++k) memcpy(tab.data() + (size_t)k * e->T_cap, srcs[k], T * sizeof(float));
+    for (int i = 0; i <= T; ++i) nl[i] = static_cast<float>(sqrt_ac_prev[i]);     // FloatTensor([f64]) rounding, diffusion.py:153
+    e->logvar_host.assign(lv, lv + T);
+    CK(cudaMemcpyAsync(e->post_tab, tab.data(), tab.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->nl_table, nl.data(), nl.size() * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_unet_forward(sr3_engine* e, const float* x, const float* noise_level, float* eps, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x && noise_level && eps, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->load_nchw(x, e->cfg.in_channel, 0, nullptr, st);
+    CK(cudaMemcpyAsync(e->nl_buf, noise_level, e->B * 4, cudaMemcpyDeviceToDevice, st));
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 0; c.out_mode = 0; c.t_next = 0;
+    e->push_ctl(st);
+    e->run_step(st);
+    CK(cudaMemcpyAsync(eps, e->eps_buf, e->img_bytes(), cudaMemcpyDeviceToDevice, st));
+    API_END
+}
+
+int sr3_p_mean_variance(sr3_engine* e, const float* x, const float* cond, int t, int clip, float* mean, float* log_variance, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x && mean, "null argument");
+    REQUIRE(e->T > 0, "set_new_noise_schedule has not been called");
+    REQUIRE(t >= 0 && t < e->T, "t=%d out of range [0,%d)", t, e->T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->load_inputs(x, cond, st);
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 1; c.out_mode = 1; c.write_mean = 1; c.update_state = 0; c.use_noise_buf = 1; c.clip = clip; c.t_next = t;
+    CK(cudaMemsetAsync(e->noise_buf, 0, e->img_bytes(), st));
+    e->push_ctl(st);
+    e->run_step(st);
+    CK(cudaMemcpyAsync(mean, e->mean_buf, e->img_bytes(), cudaMemcpyDeviceToDevice, st));
+    if (log_variance) *log_variance = e->logvar_host[t];
+    API_END
+}
+
+int sr3_p_sample(sr3_engine* e, const float* x, const float* cond, int t, const float* noise, uint64_t seed, uint64_t first_index,
+                 float* x_prev, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x && x_prev, "null argument");
+    REQUIRE(e->T > 0, "set_new_noise_schedule has not been called");
+    REQUIRE(t >= 0 && t < e->T, "t=%d out of range [0,%d)", t, e->T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->load_inputs(x, cond, st);
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 1; c.out_mode = 1; c.update_state = 1; c.clip = 1; c.t_next = t; c.seed = seed; c.sample_offset = first_index;
+    if (noise) { c.use_noise_buf = 1; CK(cudaMemcpyAsync(e->noise_buf, noise, e->img_bytes(), cudaMemcpyDeviceToDevice, st)); }
+    e->push_ctl(st);
+    e->run_step(st);
+    CK(cudaMemcpyAsync(x_prev, e->x_state, e->img_bytes(), cudaMemcpyDeviceToDevice, st));
+    API_END
+}
+
+int sr3_p_sample_loop_begin(sr3_engine* e, const float* cond, const float* x_T, uint64_t seed, uint64_t first_index, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x_T, "null argument");
+    REQUIRE(e->T > 0, "set_new_noise_schedule has not been called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->load_inputs(x_T, cond, st);
+    e->seed = seed; e->first_index = first_index;
+    API_END
+}
+int sr3_p_sample_steps(sr3_engine* e, int t_start, int steps, void* stream) {
+    API_BEGIN
+    REQUIRE(e, "null engine");
+    REQUIRE(t_start < e->T && steps >= 0 && t_start - steps + 1 >= 0, "bad step range t_start=%d steps=%d T=%d", t_start, steps, e->T);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 1; c.out_mode = 1; c.update_state = 1; c.clip = 1; c.t_next = t_start; c.seed = e->seed; c.sample_offset = e->first_index;
+    e->push_ctl(st);
+    for (int i = 0; i < steps; ++i) e->run_step(st);
+    API_END
+}
+int sr3_read_state(sr3_engine* e, float* x_out, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x_out, "null argument");
+    CK(cudaMemcpyAsync(x_out, e->x_state, e->img_bytes(), cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    API_END
+}
+
+int sr3_p_sample_loop(sr3_engine* e, const float* cond, const float* x_T, const float* noises, uint64_t seed, uint64_t first_index,
+                      float* final, float* snapshots, int snapshot_cap, int* n_snapshots, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x_T, "null argument");
+    REQUIRE(e->T > 0, "set_new_noise_schedule has not been called");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    e->load_inputs(x_T, cond, st);
+    const int T = e->T;
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 1; c.out_mode = 1; c.update_state = 1; c.clip = 1; c.t_next = T - 1; c.seed = seed; c.sample_offset = first_index;
+    c.use_noise_buf = noises ? 1 : 0;
+    e->push_ctl(st);
+    const int inter = 1 | (T / 10);                     // diffusion.py:179
+    const size_t ib = e->img_bytes();
+    int ns = 0;
+    for (int i = T - 1; i >= 0; --i) {
+        if (noises) CK(cudaMemcpyAsync(e->noise_buf, noises + (size_t)i * (ib / 4), ib, cudaMemcpyDeviceToDevice, st));
+        e->run_step(st);
+        if (i % inter == 0) {
+            if (snapshots) {
+                REQUIRE(ns < snapshot_cap, "snapshot buffer too small (%d)", snapshot_cap);
+                CK(cudaMemcpyAsync(snapshots + (size_t)ns * (ib / 4), e->x_state, ib, cudaMemcpyDeviceToDevice, st));
+            }
+            ++ns;
+        }
+    }
+    if (final) CK(cudaMemcpyAsync(final, e->x_state, ib, cudaMemcpyDeviceToDevice, st));
+    if (n_snapshots) *n_snapshots = ns;
+    API_END
+}
+
+int sr3_super_resolution_host(sr3_engine* e, const float* cond_host, const float* x_T_host, uint64_t seed, uint64_t first_index,
+                              float* final_host, void* stream) {
+    API_BEGIN
+    REQUIRE(e && x_T_host && final_host, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    const size_t ib = e->img_bytes();
+    if (cond_host) CK(cudaMemcpyAsync(e->io_a, cond_host, ib, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(e->io_b, x_T_host, ib, cudaMemcpyHostToDevice, st));
+    int ns = 0;
+    int rc = sr3_p_sample_loop(e, cond_host ? e->io_a : nullptr, e->io_b, nullptr, seed, first_index, nullptr, nullptr, 0, &ns, stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(final_host, e->x_state, ib, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_engine_num_launches_per_step(const sr3_engine* e) { return e ? (int)e->ops.size() : 0; }
+int64_t sr3_engine_workspace_bytes(const sr3_engine* e) { return e ? e->mem.bytes : 0; }
+
+int sr3_engine_read_activation(sr3_engine* e, const char* name, float* dst, int64_t cap, int64_t* numel, int shape_bhwc[4], void* stream) {
+    API_BEGIN
+    REQUIRE(e && name, "null argument");
+    auto it = e->taps.find(name);
+    REQUIRE(it != e->taps.end(), "no activation tap named %s", name);
+    const Act& a = it->second;
+    const int64_t n = (int64_t)e->B * a.H * a.W * a.C;
+    if (numel) *numel = n;
+    if (shape_bhwc) { shape_bhwc[0] = e->B; shape_bhwc[1] = a.H; shape_bhwc[2] = a.W; shape_bhwc[3] = a.C; }
+    if (dst) {
+        REQUIRE(cap >= n, "destination too small");
+        CK(cudaMemcpyAsync(dst, a.p, n * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    }
+    API_END
+}
+
+int sr3_test_gemm(const void* a, const void* b, float* dptr, int M, int N, int K, int block_n, void* stream) {
+    API_BEGIN
+    REQUIRE(M % 128 == 0 && K % 64 == 0 && N % block_n == 0, "bad test gemm shape");
+    DevAllocs mem;
+    GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(a, 1, M, K, K, 0);
+    for (int c = 0; c < K; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
+    d.block_n = block_n; d.b_ptr = b; d.b_K = K; d.b_rows = N;
+    d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = M / 128; d.tiles_h = 1; d.tiles_b = 1; d.n_tiles = N / block_n; d.nz = 1;
+    d.OW = M; d.OH = 1; d.OB = 1; d.n_valid = N;
+    d.out_f32 = dptr; d.os = OutSpec{0, 0, 0, N, 0};
+    Op op = make_gemm_op(d, mem);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    op(st);
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout,
+                  int ksize, int stride, void* stream) {
+    API_BEGIN
+    REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && Cout % 64 == 0, "bad test conv shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevAllocs mem;
+    const int ktot = ksize * ksize * Cin;
+    bf16* wp = static_cast<bf16*>(mem.alloc((size_t)Cout * ktot * 2));
+    pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w_oihw, wp, Cout, Cin, ksize, ksize, ktot, 0, Cin);
+    CK(cudaGetLastError());
+    const int OH = H / stride, OW = W / stride;
+    GemmDesc d; d.n_a = 1;
+    d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
+    add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
+    d.block_n = pick_block_n(Cout); d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
+    pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
+    REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
+    d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = B / d.b_box; d.n_tiles = Cout / d.block_n;
+    d.OW = OW; d.OH = OH; d.OB = B; d.n_valid = Cout; d.bias = bias;
+    d.out_f32 = y; d.os = nhwc_out(OH, OW, Cout);
+    d.stats = stats; d.stats_C = Cout;
+    Op op = make_gemm_op(d, mem);
+    op(st);
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,371 @@
+// Implicit-GEMM tile kernel for sm_100a (tcgen05 + TMEM + TMA), the one tensor-core kernel of the SR3 path.
+//
+//   D[128 pixels x BLOCK_N] = sum_k  A_k[128 x 64] * B_k[BLOCK_N x 64]^T        (bf16 x bf16 -> fp32 in TMEM)
+//
+// * A rows are the pixels of a (w_box x h_box x b_box) patch of an NHWC bf16 tensor, fetched by TMA as a 5-D box
+//   {64 ch, w_box, 1, h_box, b_box}; a conv tap is just the same box shifted by (dh, dw) -- out-of-image pixels are
+//   zero-filled by TMA, which is exactly conv padding.  No im2col buffer exists anywhere.
+//   The 5-D view (C', W', P, H', B) lets one kernel also do stride-2 convs (P = row parity, column parity folded into C')
+//   and plain / batched matrices (attention), see engine.cu.
+// * B rows are output channels (or keys / head-dim for attention) of a K-major bf16 matrix, 2-D TMA box {64, BLOCK_N}.
+// * The K loop is table driven (one int4 per 64-wide K slab: which A map, channel coord, tap shift, B column), so
+//   3x3 taps, the 1x1 residual conv accumulated into the same TMEM tile, and channel concats are all "more K slabs".
+// * Warp roles: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread tcgen05.mma issuer, warps 2..5 = epilogue
+//   (tcgen05.ld -> bias / FiLM / residual -> fp32 and/or bf16 NHWC stores -> per-(image,channel) GroupNorm partial sums
+//   by a transposing warp-shuffle reduction + one atomicAdd per channel per warp).
+// * The last UNet conv (Cout = 3) uses the posterior epilogue: eps -> x0 -> clamp -> posterior mean -> + sigma_t * z
+//   (model/sr3_modules/diffusion.py:141-174 of the reference) and writes x_{t-1} straight into the next step's input.
+#pragma once
+#include <cuda.h>
+#include "ptx.cuh"
+
+namespace sr3 {
+
+struct OutSpec {
+    long long sZ, sB, sH, sW, off;   // element strides: gemm-batch, image, row, column; constant offset
+};
+
+// Device-resident control block: everything that changes between launches of the (captured) step graph.
+struct StepCtl {
+    int t_cur;            // timestep of the running step
+    int t_next;           // timestep the next step_begin will load
+    int nl_from_table;    // 1: noise level = sqrt_alphas_cumprod_prev[t+1] (sampling); 0: read nl_buf[b]
+    int out_mode;         // 0: write eps (UNet.forward); 1: posterior update (p_sample)
+    int use_noise_buf;    // 1: z from noise_buf; 0: Philox
+    int write_mean;       // 1: also store the posterior mean (p_mean_variance)
+    int clip;             // clip_denoised
+    int update_state;     // 1: write x_{t-1} into x_state and the UNet input buffer
+    unsigned long long seed;
+    unsigned long long sample_offset;   // global index of image 0 (multi-GPU sharding keeps streams rank independent)
+};
+
+struct PostParams {
+    const float* tab;         // [5][T]: sqrt_recip_ac, sqrt_recipm1_ac, post_coef1, post_coef2, post_logvar_clipped
+    int T;
+    int H, W, C;              // image geometry, C = sample channels (3)
+    float* x_state;           // [B,C,H,W] fp32 NCHW
+    float* eps_out;           // [B,C,H,W]
+    float* mean_out;          // [B,C,H,W]
+    const float* noise_buf;   // [B,C,H,W]
+    __nv_bfloat16* in_buf;    // NHWC bf16 UNet input, channel stride in_C, x_t lives at channels [in_coff, in_coff+C)
+    int in_C, in_coff;
+};
+
+struct GemmParams {
+    CUtensorMap a_map[2];
+    CUtensorMap b_map;
+    const int4* ktab;        // [num_k] {a_sel, a_chan, dw | dh<<8 | p<<16, b_col}
+    int num_k;
+    int tiles_w, tiles_h, tiles_b;
+    int w_box, h_box, b_box;
+    int a_zstep, b_zrows;
+    int stages;
+    // epilogue
+    int mode;                // 0 normal, 1 final conv (eps / posterior)
+    int OW, OH, OB, n_valid;
+    float scale;
+    const float* bias;
+    const float* bias2;      // per-image bias (FiLM + conv bias), bias2[img * bias2_stride + n]
+    int bias2_stride;
+    const float* resid;
+    OutSpec rs;
+    float* out_f32;
+    OutSpec os;
+    __nv_bfloat16* out_bf16;
+    OutSpec hs;
+    float* stats;            // [B][stats_C][2] (sum, sumsq), channel offset stats_coff
+    int stats_C, stats_coff;
+    const StepCtl* ctl;
+    PostParams post;
+};
+
+constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_MAX_STAGES = 8;
+constexpr int GEMM_A_BYTES = 128 * 128;
+
+__host__ __device__ constexpr int gemm_stage_bytes(int block_n) { return GEMM_A_BYTES + block_n * 128; }
+__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
+    return stages * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
+__device__ __forceinline__ void philox4x32_10(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, float& z1) {
+    const float u1 = (static_cast<float>(a) + 1.0f) * 2.3283064365386963e-10f;   // (0, 1]
+    const float u2 = static_cast<float>(b) * 2.3283064365386963e-10f;            // [0, 1)
+    const float r = sqrtf(-2.0f * logf(u1));
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    z0 = r * c; z1 = r * s;
+}
+
+// Transposing warp reduction: every lane holds v[0..31] (one row, 32 columns); afterwards lane l returns the sum over the
+// 32 lanes (rows) of column l.  31 shuffles instead of 32 x 5.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32]) {
+    const uint32_t lane = lane_id();
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool up = (lane & half) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float keep = up ? v[j + half] : v[j];
+            const float send = up ? v[j] : v[j + half];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+        }
+    }
+    return v[0];
+}
+
+__device__ __forceinline__ long long out_index(const OutSpec& s, int z, int img, int oh, int ow) {
+    return s.off + static_cast<long long>(z) * s.sZ + static_cast<long long>(img) * s.sB + static_cast<long long>(oh) * s.sH +
+           static_cast<long long>(ow) * s.sW;
+}
+
+// reference: predict_start_from_noise + clamp + q_posterior + p_sample noise add (diffusion.py:141-174)
+__device__ __forceinline__ void final_epilogue(const GemmParams& p, const float (&eps)[4], int img, int oh, int ow) {
+    const PostParams& q = p.post;
+    const StepCtl ctl = *p.ctl;
+    const long long plane = static_cast<long long>(q.H) * q.W;
+    const long long pix = static_cast<long long>(oh) * q.W + ow;
+    if (ctl.out_mode == 0) {
+        for (int c = 0; c < q.C; ++c) q.eps_out[(static_cast<long long>(img) * q.C + c) * plane + pix] = eps[c];
+        return;
+    }
+    const int t = ctl.t_cur;
+    const float c1 = q.tab[t], c2 = q.tab[q.T + t], pc1 = q.tab[2 * q.T + t], pc2 = q.tab[3 * q.T + t];
+    const float sigma = (t > 0) ? expf(0.5f * q.tab[4 * q.T + t]) : 0.0f;
+    float z[4] = {0.f, 0.f, 0.f, 0.f};
+    if (t > 0) {
+        if (ctl.use_noise_buf) {
+            for (int c = 0; c < q.C; ++c) z[c] = q.noise_buf[(static_cast<long long>(img) * q.C + c) * plane + pix];
+        } else {
+            uint32_t ctr[4] = {static_cast<uint32_t>(pix), static_cast<uint32_t>(ctl.sample_offset + img), static_cast<uint32_t>(t),
+                               static_cast<uint32_t>((ctl.sample_offset + img) >> 32)};
+            philox4x32_10(ctr, static_cast<uint32_t>(ctl.seed), static_cast<uint32_t>(ctl.seed >> 32));
+            box_muller(ctr[0], ctr[1], z[0], z[1]);
+            box_muller(ctr[2], ctr[3], z[2], z[3]);
+        }
+    }
+    for (int c = 0; c < q.C; ++c) {
+        const long long idx = (static_cast<long long>(img) * q.C + c) * plane + pix;
+        const float xt = q.x_state[idx];
+        float x0 = __fsub_rn(__fmul_rn(c1, xt), __fmul_rn(c2, eps[c]));
+        if (ctl.clip) x0 = fminf(fmaxf(x0, -1.0f), 1.0f);
+        const float mean = __fadd_rn(__fmul_rn(pc1, x0), __fmul_rn(pc2, xt));
+        if (ctl.write_mean) q.mean_out[idx] = mean;
+        const float xn = __fadd_rn(mean, __fmul_rn(z[c], sigma));
+        if (ctl.update_state) {
+            q.x_state[idx] = xn;
+            q.in_buf[(static_cast<long long>(img) * plane + pix) * q.in_C + q.in_coff + c] = __float2bfloat16_rn(xn);
+        }
+    }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
+    constexpr int B_BYTES = BLOCK_N * 128;
+    constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t IDESC = umma_idesc_bf16(128, BLOCK_N);
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    uint8_t* base_ptr = smem_raw + (base - raw);
+    const int stages = p.stages;
+    const uint32_t bar_base = base + stages * STAGE_BYTES;
+    // barriers: full[0..8) empty[8..16) tmem_full[16]; tmem slot at +17*8
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
+    const uint32_t tmem_full_bar = bar_base + 8u * (2 * GEMM_MAX_STAGES);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + stages * STAGE_BYTES + 8 * (2 * GEMM_MAX_STAGES + 1));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    const int tm = blockIdx.x;
+    const int tw = tm % p.tiles_w;
+    const int th = (tm / p.tiles_w) % p.tiles_h;
+    const int tb = tm / (p.tiles_w * p.tiles_h);
+    const int z = blockIdx.z;
+    const int w0 = tw * p.w_box, h0 = th * p.h_box, b0 = tb * p.b_box + z * p.a_zstep;
+    const int n0 = blockIdx.y * BLOCK_N;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.a_map[0]);
+        tma_prefetch_desc(&p.a_map[1]);
+        tma_prefetch_desc(&p.b_map);
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA producer
+            for (int k = 0; k < p.num_k; ++k) {
+                const int s = k % stages;
+                const uint32_t ph = (k / stages) & 1;
+                mbar_wait(empty_bar(s), ph ^ 1u, 1);
+                const int4 e = __ldg(&p.ktab[k]);
+                const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
+                const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
+                const int pp = (e.z >> 16) & 0xff;
+                const uint32_t a_dst = base + s * STAGE_BYTES;
+                mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+                tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
+                tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, n0 + z * p.b_zrows);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------------------------ MMA issuer (one thread)
+            for (int k = 0; k < p.num_k; ++k) {
+                const int s = k % stages;
+                const uint32_t ph = (k / stages) & 1;
+                mbar_wait(full_bar(s), ph, 2);
+                tc_fence_after();
+                const uint32_t a_addr = base + s * STAGE_BYTES;
+                const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
+                const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + GEMM_A_BYTES, 1024);
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
+                    umma_bf16_ss(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
+                umma_commit(empty_bar(s));
+            }
+            umma_commit(tmem_full_bar);
+        }
+    } else {
+        // ---------------------------------------------------- epilogue: 4 warps, one TMEM lane quadrant each
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int w = row % p.w_box;
+        const int h = (row / p.w_box) % p.h_box;
+        const int bb = row / (p.w_box * p.h_box);
+        const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
+        const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
+        mbar_wait(tmem_full_bar, 0, 3);
+        tc_fence_after();
+        const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+        if constexpr (BLOCK_N == 16) {
+            uint32_t v[16];
+            tmem_ld_32x16(t_lane, v);
+            tmem_ld_wait();
+            if (row_ok) {
+                float eps[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int c = 0; c < p.post.C; ++c) eps[c] = __uint_as_float(v[c]) + __ldg(&p.bias[c]);
+                final_epilogue(p, eps, img, oh, ow);
+            }
+        } else {
+            const float* bias2 = p.bias2 ? p.bias2 + static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride : nullptr;
+            const long long ro = p.resid ? out_index(p.rs, z, img, oh, ow) : 0;
+            const long long oo = p.out_f32 ? out_index(p.os, z, img, oh, ow) : 0;
+            const long long ho = p.out_bf16 ? out_index(p.hs, z, img, oh, ow) : 0;
+#pragma unroll 1
+            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+                uint32_t v[32];
+                tmem_ld_32x32(t_lane + ch * 32, v);
+                tmem_ld_wait();
+                const int nb = n0 + ch * 32;
+                float f[32];
+                const bool full = (nb + 32 <= p.n_valid);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    float x = __uint_as_float(v[j]) * p.scale;
+                    if (full || nb + j < p.n_valid) {
+                        if (p.bias) x += __ldg(&p.bias[nb + j]);
+                        if (bias2) x += __ldg(&bias2[nb + j]);
+                    } else {
+                        x = 0.f;
+                    }
+                    f[j] = x;
+                }
+                if (row_ok && p.resid) {
+                    if (full) {
+                        const float4* r4 = reinterpret_cast<const float4*>(p.resid + ro + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 r = __ldg(&r4[j]);
+                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
+                    }
+                }
+                if (row_ok && p.out_f32) {
+                    if (full) {
+                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
+                    }
+                }
+                if (row_ok && p.out_bf16) {
+                    if (full) {
+                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            __nv_bfloat162 h0v = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                            __nv_bfloat162 h1v = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                            __nv_bfloat162 h2v = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                            __nv_bfloat162 h3v = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                            uint4 u;
+                            u.x = *reinterpret_cast<uint32_t*>(&h0v); u.y = *reinterpret_cast<uint32_t*>(&h1v);
+                            u.z = *reinterpret_cast<uint32_t*>(&h2v); u.w = *reinterpret_cast<uint32_t*>(&h3v);
+                            o4[j] = u;
+                        }
+                    } else {
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
+                    }
+                }
+                if (p.stats) {
+                    // every row of this warp belongs to the same image (w_box*h_box is a multiple of 32)
+                    float s1[32], s2[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = row_ok ? f[j] : 0.f;
+                        s1[j] = x; s2[j] = x * x;
+                    }
+                    const float cs = warp_column_sums(s1);
+                    const float cq = warp_column_sums(s2);
+                    const int img0 = __shfl_sync(0xffffffffu, img, 0);
+                    if (img0 < p.OB && nb + lane < p.n_valid) {
+                        float* st = p.stats + (static_cast<long long>(img0) * p.stats_C + p.stats_coff + nb + lane) * 2;
+                        atomicAdd(st, cs);
+                        atomicAdd(st + 1, cq);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+}  // namespace sr3

@@ -1,0 +1,117 @@
+/* sr3_b200 -- C ABI of the B200-native SR3 hot path (libsr3_b200.so).
+ *
+ * The reference (Janspiry/Image-Super-Resolution-via-Iterative-Refinement) is pure Python/PyTorch and has no
+ * FFI; its boundary for this path is the Python factory model/networks.py:83-116 `define_G(opt)` and the methods of
+ * the module it returns.  Each entry point below replaces the reference function cited next to it, with the same
+ * argument meaning, on plain device pointers (fp32, NCHW contiguous, exactly the tensors the reference passes).
+ * No torch types appear here; `stream` is a cudaStream_t passed as void*.  All functions return 0 on success and a
+ * non-zero code otherwise, with a message available from sr3_last_error().  There is no CPU fallback.
+ *
+ * Binding shown in INTEGRATION.md (ctypes, what a maintainer of the reference would add to model/networks.py).
+ */
+#ifndef SR3_B200_H
+#define SR3_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SR3_MAX_LEVELS 8
+
+/* opt['model']['unet'] + opt['model']['diffusion'] as consumed by define_G (model/networks.py:83-109) */
+typedef struct sr3_unet_config {
+    int in_channel;                    /* 6 conditional, 3 unconditional */
+    int out_channel;                   /* 3 */
+    int inner_channel;                 /* 64 (must be a multiple of 64) */
+    int norm_groups;                   /* 32 (define_G default, networks.py:89-90) or 16 */
+    int n_mults;
+    int channel_mults[SR3_MAX_LEVELS]; /* channel_multiplier */
+    int n_attn_res;
+    int attn_res[SR3_MAX_LEVELS];
+    int res_blocks;
+    int image_size;
+    int channels;                      /* diffusion.channels (3) */
+    int conditional;                   /* diffusion.conditional */
+} sr3_unet_config;
+
+typedef struct sr3_engine sr3_engine;
+
+/* Message of the last failure on the calling thread ("" if none). */
+const char* sr3_last_error(void);
+/* ABI version of this header. */
+int sr3_abi_version(void);
+
+/* UNet.__init__ (model/sr3_modules/unet.py:161-233) + GaussianDiffusion.__init__ (diffusion.py:64-82):
+ * builds the layer plan, allocates activations / packed weights on `device` for a fixed batch size. */
+int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out);
+void sr3_engine_destroy(sr3_engine* e);
+
+/* Parameter table in the reference's state_dict order and naming ("downs.1.res_block.block1.block.3.weight", ...;
+ * keys are relative to denoise_fn).  shape has up to 4 entries (OIHW for convs). */
+int sr3_engine_num_params(const sr3_engine* e);
+int sr3_engine_param_info(const sr3_engine* e, int index, char* name, int name_cap, int64_t shape[4], int* ndim);
+/* load_state_dict for one tensor (model/model.py:146-160): `src` is a DEVICE fp32 pointer in the reference layout.
+ * Weights are re-packed (OIHW -> K-major bf16) by a kernel on `stream`. */
+int sr3_engine_load_param(sr3_engine* e, const char* name, const float* src, int64_t numel, void* stream);
+/* Must be called after the last load_param of a batch of updates (fuses bias vectors). */
+int sr3_engine_finalize_params(sr3_engine* e, void* stream);
+
+/* set_new_noise_schedule (model/sr3_modules/diffusion.py:92-139): HOST pointers to the fp32 buffers
+ * sqrt_recip_alphas_cumprod, sqrt_recipm1_alphas_cumprod, posterior_mean_coef1, posterior_mean_coef2,
+ * posterior_log_variance_clipped (each [T]) and the float64 sqrt_alphas_cumprod_prev ([T+1]). */
+int sr3_engine_set_schedule(sr3_engine* e, int T, const float* sqrt_recip_ac, const float* sqrt_recipm1_ac, const float* post_coef1,
+                            const float* post_coef2, const float* post_logvar, const double* sqrt_ac_prev, void* stream);
+
+/* UNet.forward (model/sr3_modules/unet.py:235-259): x [B,in_channel,H,W], noise_level [B] (the reference's [B,1]) -> eps
+ * [B,out_channel,H,W].  All DEVICE fp32. */
+int sr3_unet_forward(sr3_engine* e, const float* x, const float* noise_level, float* eps, void* stream);
+
+/* p_mean_variance (diffusion.py:151-167): x [B,3,H,W], condition_x [B,3,H,W] or NULL, integer t -> posterior mean
+ * [B,3,H,W] (DEVICE) and the clipped log-variance (HOST scalar, may be NULL). */
+int sr3_p_mean_variance(sr3_engine* e, const float* x, const float* condition_x, int t, int clip_denoised, float* mean, float* log_variance,
+                        void* stream);
+
+/* p_sample (diffusion.py:169-174): x_{t-1} = mean + exp(0.5 logvar) * z for t > 0.  `noise` (DEVICE [B,3,H,W]) replaces
+ * torch.randn_like when non-NULL; otherwise z comes from Philox4x32-10 keyed by (seed, first_sample_index + b, pixel, t). */
+int sr3_p_sample(sr3_engine* e, const float* x, const float* condition_x, int t, const float* noise, uint64_t seed,
+                 uint64_t first_sample_index, float* x_prev, void* stream);
+
+/* p_sample_loop / super_resolution / sample (diffusion.py:176-210): runs t = T-1 .. 0 as T launches of one captured CUDA
+ * graph.  x_T: DEVICE [B,3,H,W] initial noise (the reference's torch.randn(shape)).  noises: optional DEVICE
+ * [T][B,3,H,W], noises[i] used at step i.  Every (i % (1|T/10) == 0) the image is appended to `snapshots`
+ * (DEVICE [n][B,3,H,W], capacity snapshot_cap images-batches; may be NULL) -- the `continous=True` return value without
+ * its first B rows.  final: DEVICE [B,3,H,W] = x_0.  *n_snapshots receives the count. */
+int sr3_p_sample_loop(sr3_engine* e, const float* condition_x, const float* x_T, const float* noises, uint64_t seed,
+                      uint64_t first_sample_index, float* final, float* snapshots, int snapshot_cap, int* n_snapshots, void* stream);
+
+/* Same loop on HOST buffers (H2D of condition_x / x_T, D2H of final inside): the end-to-end entry point. */
+int sr3_super_resolution_host(sr3_engine* e, const float* condition_x_host, const float* x_T_host, uint64_t seed,
+                              uint64_t first_sample_index, float* final_host, void* stream);
+
+/* Run `steps` reverse steps starting at timestep t_start on the engine's resident state (benchmark / profiling hook:
+ * no copies, no snapshots).  State must have been initialised by sr3_p_sample_loop_begin. */
+int sr3_p_sample_loop_begin(sr3_engine* e, const float* condition_x, const float* x_T, uint64_t seed, uint64_t first_sample_index, void* stream);
+int sr3_p_sample_steps(sr3_engine* e, int t_start, int steps, void* stream);
+int sr3_read_state(sr3_engine* e, float* x_out, void* stream);
+
+/* Introspection for tests / bench. */
+int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernels in the captured step graph */
+int64_t sr3_engine_workspace_bytes(const sr3_engine* e);
+/* Debug tap: copy the fp32 NHWC output of top-level layer `name` ("downs.3", "mid.0", ...) of the last forward to dst
+ * (DEVICE, [B,H,W,C]); returns C*H*W*B through *numel. */
+int sr3_engine_read_activation(sr3_engine* e, const char* name, float* dst, int64_t cap, int64_t* numel, int shape_bhwc[4], void* stream);
+
+/* Stand-alone tile GEMM for unit tests: D[M,N] = A[M,K] * B[N,K]^T (bf16 row-major DEVICE inputs, fp32 output), M%128==0,
+ * K%64==0, N%block_n==0. */
+int sr3_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, int block_n, void* stream);
+/* Stand-alone NHWC conv for unit tests: x bf16 [B,H,W,Cin], w fp32 OIHW [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
+ * y fp32 [B,OH,OW,Cout]; stats (optional) fp32 [B,Cout,2] must be zeroed by the caller. */
+int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin,
+                  int Cout, int ksize, int stride, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SR3_B200_H */

@@ -1,0 +1,46 @@
+"""GPU parity of the single tensor-core tile kernel (tcgen05 + TMA) against fp32 torch references on CPU,
+called through the C ABI (sr3_test_gemm / sr3_test_conv)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 64, 64, 64), (128, 128, 128, 128), (256, 256, 192, 256), (384, 128, 1024, 64),
+                                      (1024, 512, 4608, 128), (128, 16, 576, 16)])
+def test_gemm_matches_fp32(M, N, K, bn):
+    from sr3_b200 import _native
+    g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn(M, K, generator=g).bfloat16()
+    b = torch.randn(N, K, generator=g).bfloat16()
+    if bn == 16:
+        pytest.skip("block_n 16 is the final-conv epilogue only")
+    d = _native.test_gemm(a.cuda(), b.cuda(), bn).cpu()
+    ref = a.float() @ b.float().t()
+    assert rel(d, ref) < 2e-5, rel(d, ref)
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,k,s", [
+    (2, 16, 16, 64, 64, 1, 1), (2, 16, 16, 64, 64, 3, 1), (2, 8, 8, 128, 128, 3, 1), (1, 32, 32, 64, 128, 3, 1),
+    (2, 32, 32, 192, 64, 3, 1), (2, 16, 16, 64, 64, 3, 2), (1, 64, 64, 128, 128, 3, 2), (2, 128, 128, 64, 64, 3, 1),
+    (4, 8, 8, 512, 512, 3, 1), (2, 16, 16, 1024, 512, 1, 1)])
+def test_conv_matches_fp32(B, H, W, Cin, Cout, k, s):
+    from sr3_b200 import _native
+    g = torch.Generator().manual_seed(B + H * 3 + Cin * 5 + Cout * 7 + k + s)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16()
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)
+    bias = torch.randn(Cout, generator=g)
+    y, stats = _native.test_conv(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), bias.cuda(), k, s, want_stats=True)
+    y = y.cpu().permute(0, 3, 1, 2)
+    ref = F.conv2d(x.float(), w.bfloat16().float(), bias, stride=s, padding=k // 2)
+    assert y.shape == ref.shape
+    assert rel(y, ref) < 2e-5, rel(y, ref)
+    # GroupNorm partial sums accumulated by the epilogue
+    st = stats.cpu()
+    assert torch.allclose(st[..., 0], ref.sum(dim=(2, 3)), rtol=1e-3, atol=1e-2)
+    assert torch.allclose(st[..., 1], (ref * ref).sum(dim=(2, 3)), rtol=1e-3, atol=1e-2)
