@@ -41,6 +41,8 @@ _SIGS = {
     "sr3_p_sample_loop_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p]),
     "sr3_p_sample_steps": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "sr3_read_state": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "sr3_engine_profile_step": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_float), POINTER(c_double), POINTER(c_double),
+                                        POINTER(c_int), c_void_p]),
     "sr3_engine_num_launches_per_step": (c_int, [c_void_p]),
     "sr3_engine_workspace_bytes": (c_int64, [c_void_p]),
     "sr3_engine_read_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int), c_void_p]),
@@ -233,6 +235,16 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(lib().sr3_read_state(self._h, _ptr(out), _stream()))
         return out
+
+    def profile_step(self, t, reps=3):
+        """[(kind, ms, flops, bytes)] per launch of one eager step (kinds: 0 gemm tile, 1 GN apply, 2 cast, 3 softmax, 4 other)."""
+        cap = self.launches_per_step()
+        kinds, ms = (c_int * cap)(), (c_float * cap)()
+        fl, by = (c_double * cap)(), (c_double * cap)()
+        n = c_int()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_engine_profile_step(self._h, int(t), int(reps), cap, kinds, ms, fl, by, ctypes.byref(n), _stream()))
+        return [(kinds[i], ms[i], fl[i], by[i]) for i in range(n.value)]
 
     def launches_per_step(self):
         return lib().sr3_engine_num_launches_per_step(self._h)

@@ -281,6 +281,8 @@ struct sr3_engine {
     std::vector<ParamEntry> params;
     std::map<std::string, int> pindex;
     std::vector<Op> ops, finalize_ops;
+    struct OpInfo { int kind; double flops; double bytes; };   // kind: 0 gemm, 1 groupnorm-apply, 2 cast/upsample, 3 softmax, 4 other
+    std::vector<OpInfo> op_info;
     std::map<std::string, Act> taps;
     std::map<std::string, size_t> role_max;
     std::map<std::string, void*> role_ptr;
@@ -367,7 +369,25 @@ struct sr3_engine {
         const int rows_pad = ((rows + block_n - 1) / block_n) * block_n;
         return static_cast<bf16*>(mem.alloc((size_t)rows_pad * ktot * sizeof(bf16)));
     }
-    void push(Op op) { if (!dry) ops.push_back(std::move(op)); }
+    void push(Op op, int kind = 4, double flops = 0, double bytes = 0) {
+        if (dry) return;
+        ops.push_back(std::move(op));
+        op_info.push_back({kind, flops, bytes});
+    }
+    // executed work of a gemm op: 2*M*N*K flops; bytes = A read once per tap set + B once + outputs
+    void push_gemm(const GemmDesc& d) {
+        const double M = (double)d.OW * d.OH * d.OB * (d.nz > 1 && d.a_zstep == 0 ? d.nz : 1);
+        const double K = 64.0 * d.slabs.size();
+        const double N = d.n_valid;
+        double bytes = N * K * 2;
+        if (d.out_f32) bytes += M * N * 4;
+        if (d.out_bf16) bytes += M * N * 2;
+        if (d.resid) bytes += M * N * 4;
+        double a_elems = 0;
+        for (int i = 0; i < d.n_a; ++i) a_elems += (double)d.a[i].C * d.a[i].W * d.a[i].P * d.a[i].H * d.a[i].Bn;
+        bytes += a_elems * 2;
+        push(make_gemm_op(d, mem), 0, 2.0 * M * N * K, bytes);
+    }
 
     // ---- layer builders -------------------------------------------------------------------------
     void add_prep(const Act& s0, const Act* s1, const float* gamma, const float* beta, int groups, bool silu, bf16* out_a, bf16* out_raw) {
@@ -383,14 +403,14 @@ struct sr3_engine {
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);
-        push([p, grid, smem](cudaStream_t st) { prep_kernel<<<grid, 256, smem, st>>>(p); CK(cudaGetLastError()); });
+        push([p, grid, smem](cudaStream_t st) { prep_kernel<<<grid, 256, smem, st>>>(p); CK(cudaGetLastError()); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
     }
     void add_cast(const Act& s, bf16* dst, int up) {
         if (dry) return;
         const long long total = 1LL * B * s.H * up * s.W * up * (s.C / 4);
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         const float* src = s.p; const int Bn = B, Hh = s.H, Ww = s.W, C = s.C;
-        push([=](cudaStream_t st) { cast_kernel<<<blocks, 256, 0, st>>>(src, dst, Bn, Hh, Ww, C, up); CK(cudaGetLastError()); });
+        push([=](cudaStream_t st) { cast_kernel<<<blocks, 256, 0, st>>>(src, dst, Bn, Hh, Ww, C, up); CK(cudaGetLastError()); }, 2, 0, (double)Bn * Hh * Ww * C * (4.0 + 2.0 * up * up));
     }
 
     // generic image conv: A sources already bf16; out fp32 NHWC (+stats)
@@ -418,7 +438,7 @@ struct sr3_engine {
         d.resid = c.resid; d.rs = nhwc_out(c.OH, c.OW, c.cout);
         d.out_f32 = c.out.p; d.os = nhwc_out(c.OH, c.OW, c.cout);
         d.stats = c.out.stats; d.stats_C = c.cout; d.stats_coff = 0;
-        push(make_gemm_op(d, mem));
+        push_gemm(d);
     }
 
     // ResnetBlock (+ optional SelfAttention): reference unet.py:94-158
@@ -515,7 +535,7 @@ struct sr3_engine {
             d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 2 * C / 128;
             d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = 2 * C;
             d.out_bf16 = qk; d.hs = nhwc_out(Hh, Ww, 2 * C);
-            push(make_gemm_op(d, mem));
+            push_gemm(d);
         }
         {   // vT[z][d][token] = Wv[d,:] . n[token,:]  (weights are the A operand, tokens the B operand)
             GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(wqkv + (size_t)2 * C * C, 1, C, C, C, 0);
@@ -525,7 +545,7 @@ struct sr3_engine {
             d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 0; d.b_zrows = Lt;
             d.OW = C; d.OH = 1; d.OB = 1; d.n_valid = Lt;
             d.out_bf16 = vT; d.hs = OutSpec{(long long)C * Lt, 0, 0, Lt, 0};
-            push(make_gemm_op(d, mem));
+            push_gemm(d);
         }
         {   // S[z] = q k^T / sqrt(C)
             GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C, 2 * C, (long long)Lt * 2 * C);
@@ -535,12 +555,12 @@ struct sr3_engine {
             d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = Lt;
             d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = Lt; d.scale = 1.0f / sqrtf((float)C);
             d.out_f32 = S; d.os = OutSpec{0, (long long)Lt * Lt, 0, Lt, 0};
-            push(make_gemm_op(d, mem));
+            push_gemm(d);
         }
         {
             const long long rows = (long long)nz * Lt;
             const int blocks = (int)((rows + 7) / 8);
-            push([=](cudaStream_t st) { softmax_kernel<<<blocks, 256, 0, st>>>(S, P, rows, Lt, HW); CK(cudaGetLastError()); });
+            push([=](cudaStream_t st) { softmax_kernel<<<blocks, 256, 0, st>>>(S, P, rows, Lt, HW); CK(cudaGetLastError()); }, 3, 0, (double)rows * Lt * 6.0);
         }
         {   // O[z] = P v : rows = queries, N = head dim, K = keys
             GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
@@ -550,7 +570,7 @@ struct sr3_engine {
             d.n_tiles = C / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = C;
             d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = C;
             d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C, 0, C, 0};
-            push(make_gemm_op(d, mem));
+            push_gemm(d);
         }
         {   // out projection + bias + residual (un-normalised input)
             ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(O, Bp, Hh, Ww, C);
@@ -694,7 +714,7 @@ struct sr3_engine {
                 d.post.tab = post_tab; d.post.T = T_cap; d.post.H = H; d.post.W = W; d.post.C = co;
                 d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
                 d.post.in_buf = in_buf; d.post.in_C = in_C; d.post.in_coff = cond_c;
-                push(make_gemm_op(d, mem));
+                push_gemm(d);
             }
         }
     }
@@ -968,6 +988,36 @@ int sr3_super_resolution_host(sr3_engine* e, const float* cond_host, const float
     if (rc) return rc;
     CK(cudaMemcpyAsync(final_host, e->x_state, ib, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_engine_profile_step(sr3_engine* e, int t, int reps, int cap, int* kinds, float* ms, double* flops, double* bytes, int* n_ops, void* stream) {
+    API_BEGIN
+    REQUIRE(e && kinds && ms && flops && bytes && n_ops, "null argument");
+    REQUIRE(e->T > 0 && t >= 0 && t < e->T, "bad t");
+    const int n = (int)e->ops.size();
+    REQUIRE(cap >= n, "profile buffers too small (%d ops)", n);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    std::vector<cudaEvent_t> ev(n + 1);
+    for (auto& x : ev) CK(cudaEventCreate(&x));
+    std::vector<double> acc(n, 0.0);
+    for (int r = 0; r < reps + 1; ++r) {          // first repetition is a warm-up
+        StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+        c.nl_from_table = 1; c.out_mode = 1; c.update_state = 0; c.clip = 1; c.t_next = t; c.seed = 1;
+        e->push_ctl(st);
+        for (int i = 0; i < n; ++i) { CK(cudaEventRecord(ev[i], st)); e->ops[i](st); }
+        CK(cudaEventRecord(ev[n], st));
+        CK(cudaStreamSynchronize(st));
+        if (r == 0) continue;
+        for (int i = 0; i < n; ++i) { float m = 0; CK(cudaEventElapsedTime(&m, ev[i], ev[i + 1])); acc[i] += m; }
+    }
+    for (int i = 0; i < n; ++i) {
+        kinds[i] = e->op_info[i].kind; ms[i] = (float)(acc[i] / (reps > 0 ? reps : 1));
+        flops[i] = e->op_info[i].flops; bytes[i] = e->op_info[i].bytes;
+    }
+    *n_ops = n;
+    for (auto& x : ev) cudaEventDestroy(x);
     API_END
 }
 

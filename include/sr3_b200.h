@@ -99,6 +99,11 @@ int sr3_read_state(sr3_engine* e, float* x_out, void* stream);
 /* Introspection for tests / bench. */
 int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernels in the captured step graph */
 int64_t sr3_engine_workspace_bytes(const sr3_engine* e);
+/* Per-kernel timing of one eager (non-graph) reverse step at timestep t, averaged over `reps` repetitions after one warm-up,
+ * CUDA events on `stream` around every launch.  kinds: 0 tensor-core tile kernel, 1 GroupNorm apply, 2 cast/upsample,
+ * 3 softmax, 4 other; flops / bytes are the executed work of each launch.  Does not modify the sampler state. */
+int sr3_engine_profile_step(sr3_engine* e, int t, int reps, int cap, int* kinds, float* ms, double* flops, double* bytes, int* n_ops,
+                            void* stream);
 /* Debug tap: copy the fp32 NHWC output of top-level layer `name` ("downs.3", "mid.0", ...) of the last forward to dst
  * (DEVICE, [B,H,W,C]); returns C*H*W*B through *numel. */
 int sr3_engine_read_activation(sr3_engine* e, const char* name, float* dst, int64_t cap, int64_t* numel, int shape_bhwc[4], void* stream);

