@@ -34,20 +34,21 @@ struct PrepParams {
 __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
     extern __shared__ float sm[];
     const int C = p.C0 + p.C1;
-    float* sc = sm;              // [C]
-    float* sh = sm + C;          // [C]
+    float* sc = sm;              // [C] scale   (first used as per-channel sum)
+    float* sh = sm + C;          // [C] shift   (first used as per-channel sum of squares)
     float* gm = sm + 2 * C;      // [groups] mean
     float* gr = gm + p.groups;   // [groups] rstd
     const int b = blockIdx.y;
     const int gs = C / p.groups;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float2 st = (c < p.C0) ? __ldg(reinterpret_cast<const float2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
+                                     : __ldg(reinterpret_cast<const float2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
+        sc[c] = st.x; sh[c] = st.y;
+    }
+    __syncthreads();
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
         float s = 0.f, q = 0.f;
-        for (int j = 0; j < gs; ++j) {
-            const int c = g * gs + j;
-            const float* st = (c < p.C0) ? p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2
-                                         : p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2;
-            s += st[0]; q += st[1];
-        }
+        for (int j = 0; j < gs; ++j) { s += sc[g * gs + j]; q += sh[g * gs + j]; }
         const float inv = 1.0f / (static_cast<float>(gs) * static_cast<float>(p.HW));
         const float mean = s * inv;
         const float var = fmaxf(q * inv - mean * mean, 0.f);
@@ -56,25 +57,42 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         const int g = c / gs;
-        const float k = gr[g] * p.gamma[c];
-        sc[c] = k; sh[c] = p.beta[c] - gm[g] * k;
+        const float k = gr[g] * __ldg(&p.gamma[c]);
+        sc[c] = k; sh[c] = __ldg(&p.beta[c]) - gm[g] * k;
     }
     __syncthreads();
     const int vec_per_pix = C >> 2;
     const int pix0 = blockIdx.x * p.pix_per_block;
     const int npix = min(p.pix_per_block, p.HW - pix0);
     const int total = npix * vec_per_pix;
-    for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int pix = pix0 + i / vec_per_pix;
-        const int c = (i % vec_per_pix) << 2;
-        const long long pg = static_cast<long long>(b) * p.HW + pix;
-        float4 x;
-        if (c < p.C0) x = __ldg(reinterpret_cast<const float4*>(p.src0 + pg * p.C0 + c));
-        else x = __ldg(reinterpret_cast<const float4*>(p.src1 + pg * p.C1 + (c - p.C0)));
-        float y0 = x.x * sc[c] + sh[c], y1 = x.y * sc[c + 1] + sh[c + 1], y2 = x.z * sc[c + 2] + sh[c + 2], y3 = x.w * sc[c + 3] + sh[c + 3];
-        if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-        *reinterpret_cast<uint2*>(p.out_a + pg * C + c) = pack_bf16x4(y0, y1, y2, y3);
-        if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + pg * C + c) = pack_bf16x4(x.x, x.y, x.z, x.w);
+    constexpr int U = 4;          // independent 16-byte loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+        float4 x[U];
+        long long pg[U];
+        int cc[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                const int pix = pix0 + i / vec_per_pix;
+                cc[u] = (i % vec_per_pix) << 2;
+                pg[u] = static_cast<long long>(b) * p.HW + pix;
+                x[u] = (cc[u] < p.C0) ? __ldg(reinterpret_cast<const float4*>(p.src0 + pg[u] * p.C0 + cc[u]))
+                                      : __ldg(reinterpret_cast<const float4*>(p.src1 + pg[u] * p.C1 + (cc[u] - p.C0)));
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < total) {
+                const int c = cc[u];
+                float y0 = x[u].x * sc[c] + sh[c], y1 = x[u].y * sc[c + 1] + sh[c + 1], y2 = x[u].z * sc[c + 2] + sh[c + 2],
+                      y3 = x[u].w * sc[c + 3] + sh[c + 3];
+                if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                *reinterpret_cast<uint2*>(p.out_a + pg[u] * C + c) = pack_bf16x4(y0, y1, y2, y3);
+                if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + pg[u] * C + c) = pack_bf16x4(x[u].x, x[u].y, x[u].z, x[u].w);
+            }
+        }
     }
 }
 

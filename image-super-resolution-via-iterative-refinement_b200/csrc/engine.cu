@@ -58,7 +58,8 @@ EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-CUtensorMap encode_map(int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+CUtensorMap encode_map(int rank, const void* ptr, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                       CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     CUtensorMap m;
     cuuint64_t gd[5], gs[4];
     cuuint32_t bx[5], es[5];
@@ -66,7 +67,8 @@ CUtensorMap encode_map(int rank, const void* ptr, const uint64_t* dims, const ui
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
     for (int i = 0; i < rank; ++i) REQUIRE(box[i] >= 1 && box[i] <= 256 && box[i] <= dims[i], "TMA box %u exceeds dim %llu (axis %d)", box[i], (unsigned long long)dims[i], i);
     REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base not 16B aligned");
-    CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    for (int i = 0; i < rank - 1; ++i) REQUIRE(strides_bytes[i] % 16 == 0 && strides_bytes[i] > 0, "TMA stride %llu (axis %d) must be a positive multiple of 16", (unsigned long long)strides_bytes[i], i + 1);
+    CUresult r = get_encode_fn()(&m, dtype, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu box=%u,%u", (int)r, rank,
             (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
@@ -125,16 +127,25 @@ OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
     OutSpec s; s.sZ = 0; s.sB = 1LL * H * W * C; s.sH = 1LL * W * C; s.sW = C; s.off = off; return s;
 }
 
-int pick_stages(int block_n, int num_k) {
-    int s = block_n >= 256 ? 4 : (block_n == 128 ? 3 : 4);
+constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
+int pick_stages(int block_n) {
+    int s = GEMM_MAX_STAGES;
     if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    if (s > num_k) s = num_k;
+    while (s > 1 && gemm_smem_bytes(block_n, s) > SMEM_LIMIT) --s;
     if (s < 1) s = 1;
     return s;
 }
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        CK(cudaGetDevice(&dev));
+        CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    }
+    return n;
+}
 
-constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
 template <int BN>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
     gemm_tile_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(p);
@@ -201,16 +212,49 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.tiles_w = d.tiles_w; p.tiles_h = d.tiles_h; p.tiles_b = d.tiles_b;
     p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
     p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
-    p.stages = pick_stages(d.block_n, p.num_k);
+    p.stages = pick_stages(d.block_n);
+    p.n_tiles = d.n_tiles; p.nz = d.nz;
     p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
     p.bias = d.bias; p.bias2 = d.bias2; p.bias2_stride = d.bias2_stride;
     p.resid = d.resid; p.rs = d.rs; p.out_f32 = d.out_f32; p.os = d.os; p.out_bf16 = d.out_bf16; p.hs = d.hs;
     p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
     if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
-    const dim3 grid(d.tiles_w * d.tiles_h * d.tiles_b, d.n_tiles, d.nz);
+    // fp32 output / residual through smem + TMA: one 32-row x 32-column box per epilogue warp
+    p.tma_epi = (d.mode == 0 && getenv("SR3_NO_TMA_EPI") == nullptr && (d.out_f32 || d.resid)) ? 1 : 0;
+    if (p.tma_epi) {
+        const int w_sub = d.w_box < 32 ? d.w_box : 32, h_sub = 32 / w_sub;
+        REQUIRE(d.w_box % w_sub == 0 && (d.h_box % h_sub == 0 || d.h_box == 1), "tile box %dx%d cannot be split into per-warp boxes", d.w_box, d.h_box);
+        auto mk = [&](const float* ptr, const OutSpec& o, bool& c4z) {
+            c4z = (o.sB == 0 && o.sZ != 0);
+            const long long s4 = c4z ? o.sZ : o.sB;
+            const uint64_t n4 = c4z ? (uint64_t)d.nz : (uint64_t)(d.tiles_b * d.b_box > d.OB ? d.tiles_b * d.b_box : d.OB);
+            const uint64_t dims[5] = {(uint64_t)d.n_valid, (uint64_t)d.OW, 1ull, (uint64_t)d.OH, n4};
+            uint64_t str[4];
+            str[0] = (uint64_t)o.sW * 4;
+            str[1] = str[0] * d.OW;
+            str[2] = d.OH > 1 ? (uint64_t)o.sH * 4 : str[1];
+            str[3] = s4 != 0 ? (uint64_t)s4 * 4 : str[2] * d.OH;
+            const uint32_t box[5] = {32u, (uint32_t)w_sub, 1u, (uint32_t)h_sub, 1u};
+            REQUIRE(d.n_valid >= 32, "TMA epilogue needs at least 32 output columns");
+            return encode_map(5, ptr + o.off, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+        };
+        bool zo = false, zr = false;
+        if (d.out_f32) p.out_map = mk(d.out_f32, d.os, zo);
+        if (d.resid) p.res_map = mk(d.resid, d.rs, zr);
+        if (d.out_f32 && d.resid) REQUIRE(zo == zr, "output and residual must share the batch coordinate");
+        if (!d.out_f32) p.out_map = p.res_map;
+        if (!d.resid) p.res_map = p.out_map;
+        p.epi_c4_is_z = (d.out_f32 ? zo : zr) ? 1 : 0;
+    } else {
+        p.out_map = p.b_map; p.res_map = p.b_map;
+    }
+    const int total_tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz;
+    int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
+    if (const char* e = getenv("SR3_MAX_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }
+    const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
-    while (gemm_smem_bytes(bn, p.stages) > SMEM_LIMIT && p.stages > 1) --p.stages;
     const int smem = gemm_smem_bytes(bn, p.stages);
+    REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
     REQUIRE(bn == 16 || bn == 64 || bn == 128 || bn == 256, "unsupported block_n %d", bn);
     return [p, grid, bn, smem](cudaStream_t st) {
@@ -399,7 +443,7 @@ struct sr3_engine {
         p.out_a = out_a; p.out_raw = out_raw;
         const int C = p.C0 + p.C1;
         REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
-        int ppb = 16384 / C; if (ppb < 8) ppb = 8; if (ppb > p.HW) ppb = p.HW;
+        int ppb = 4096 / C; if (ppb < 1) ppb = 1; if (ppb > p.HW) ppb = p.HW;
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);

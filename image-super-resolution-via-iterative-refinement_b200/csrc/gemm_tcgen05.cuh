@@ -54,9 +54,14 @@ struct PostParams {
 struct GemmParams {
     CUtensorMap a_map[2];
     CUtensorMap b_map;
+    CUtensorMap out_map;     // fp32 output, 5-D {N, W, 1, H, B|Z}, box {32, w_sub, 1, h_sub, 1}: one warp's 32 rows x 32 columns
+    CUtensorMap res_map;     // fp32 residual, same geometry
     const int4* ktab;        // [num_k] {a_sel, a_chan, dw | dh<<8 | p<<16, b_col}
     int num_k;
     int tiles_w, tiles_h, tiles_b;
+    int n_tiles, nz;         // persistent schedule: tile = n_tile + n_tiles * (m_tile + tiles_m * z)
+    int tma_epi;             // 1: fp32 output / residual go through smem + TMA (out_map / res_map)
+    int epi_c4_is_z;         // 5th coordinate of out_map / res_map: gemm-batch z (1) or image index (0)
     int w_box, h_box, b_box;
     int a_zstep, b_zrows;
     int stages;
@@ -82,10 +87,12 @@ struct GemmParams {
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_BYTES = 128 * 128;
+constexpr int GEMM_EPI_WARP_BYTES = 16384;   // per epilogue warp: 2 x 4 KB output staging + 2 x 4 KB residual staging
+constexpr int GEMM_EPI_BYTES = 4 * GEMM_EPI_WARP_BYTES;
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n) { return GEMM_A_BYTES + block_n * 128; }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
-    return stages * gemm_stage_bytes(block_n) + 1024 /*align slack*/ + 256 /*barriers*/;
+    return stages * gemm_stage_bytes(block_n) + GEMM_EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
@@ -170,11 +177,14 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
     }
 }
 
+// Persistent, warp-specialised tile kernel.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...; the accumulator is double
+// buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1, and the TMA producer runs ahead across tiles.
 template <int BLOCK_N>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
     constexpr int B_BYTES = BLOCK_N * 128;
     constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+    constexpr uint32_t ACC_COLS = BLOCK_N;                                  // columns per accumulator buffer
+    constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;   // two buffers, power of two >= 32
     constexpr uint32_t IDESC = umma_idesc_bf16(128, BLOCK_N);
 
     extern __shared__ uint8_t smem_raw[];
@@ -182,33 +192,36 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const __grid_co
     const uint32_t base = (raw + 1023u) & ~1023u;
     uint8_t* base_ptr = smem_raw + (base - raw);
     const int stages = p.stages;
-    const uint32_t bar_base = base + stages * STAGE_BYTES;
-    // barriers: full[0..8) empty[8..16) tmem_full[16]; tmem slot at +17*8
+    const uint32_t epi_base = base + stages * STAGE_BYTES;                  // 1024-aligned (stage sizes are multiples of 1024)
+    const uint32_t bar_base = epi_base + GEMM_EPI_BYTES;
+    // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[4 warps][2]; then the TMEM slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
-    const uint32_t tmem_full_bar = bar_base + 8u * (2 * GEMM_MAX_STAGES);
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + stages * STAGE_BYTES + 8 * (2 * GEMM_MAX_STAGES + 1));
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + a); };
+    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };
+    volatile uint32_t* tmem_slot =
+        reinterpret_cast<volatile uint32_t*>(base_ptr + stages * STAGE_BYTES + GEMM_EPI_BYTES + 8 * (2 * GEMM_MAX_STAGES + 12));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    const int tm = blockIdx.x;
-    const int tw = tm % p.tiles_w;
-    const int th = (tm / p.tiles_w) % p.tiles_h;
-    const int tb = tm / (p.tiles_w * p.tiles_h);
-    const int z = blockIdx.z;
-    const int w0 = tw * p.w_box, h0 = th * p.h_box, b0 = tb * p.b_box + z * p.a_zstep;
-    const int n0 = blockIdx.y * BLOCK_N;
+    const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
+    const int total_tiles = tiles_m * p.n_tiles * p.nz;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.a_map[0]);
         tma_prefetch_desc(&p.a_map[1]);
         tma_prefetch_desc(&p.b_map);
+        if (p.tma_epi) { tma_prefetch_desc(&p.out_map); tma_prefetch_desc(&p.res_map); }
         for (int s = 0; s < stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(tmem_full_bar, 1);
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);       // one arrive per epilogue warp
+        }
+        for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -220,40 +233,63 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const __grid_co
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    auto decode = [&](int tile, int& w0, int& h0, int& b0, int& n0, int& z) {
+        const int nt = tile % p.n_tiles;
+        const int r = tile / p.n_tiles;
+        const int tm = r % tiles_m;
+        z = r / tiles_m;
+        const int tw = tm % p.tiles_w;
+        const int th = (tm / p.tiles_w) % p.tiles_h;
+        const int tb = tm / (p.tiles_w * p.tiles_h);
+        w0 = tw * p.w_box; h0 = th * p.h_box; b0 = tb * p.b_box + z * p.a_zstep; n0 = nt * BLOCK_N;
+    };
+
     if (warp == 0) {
         if (lane == 0) {
-            // ------------------------------------------------ TMA producer
-            for (int k = 0; k < p.num_k; ++k) {
-                const int s = k % stages;
-                const uint32_t ph = (k / stages) & 1;
-                mbar_wait(empty_bar(s), ph ^ 1u, 1);
-                const int4 e = __ldg(&p.ktab[k]);
-                const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
-                const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
-                const int pp = (e.z >> 16) & 0xff;
-                const uint32_t a_dst = base + s * STAGE_BYTES;
-                mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-                tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
-                tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, n0 + z * p.b_zrows);
+            // ------------------------------------------------ TMA producer (runs ahead across tiles)
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                int w0, h0, b0, n0, z;
+                decode(tile, w0, h0, b0, n0, z);
+                for (int k = 0; k < p.num_k; ++k, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(empty_bar(s), ph ^ 1u, 1);
+                    const int4 e = __ldg(&p.ktab[k]);
+                    const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
+                    const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
+                    const int pp = (e.z >> 16) & 0xff;
+                    const uint32_t a_dst = base + s * STAGE_BYTES;
+                    mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
+                    tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
+                    tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, n0 + z * p.b_zrows);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {
             // ------------------------------------------------ MMA issuer (one thread)
-            for (int k = 0; k < p.num_k; ++k) {
-                const int s = k % stages;
-                const uint32_t ph = (k / stages) & 1;
-                mbar_wait(full_bar(s), ph, 2);
+            int it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+                const int acc = ti & 1;
+                mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t a_addr = base + s * STAGE_BYTES;
-                const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
-                const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + GEMM_A_BYTES, 1024);
+                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+                for (int k = 0; k < p.num_k; ++k, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(full_bar(s), ph, 2);
+                    tc_fence_after();
+                    const uint32_t a_addr = base + s * STAGE_BYTES;
+                    const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
+                    const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + GEMM_A_BYTES, 1024);
 #pragma unroll
-                for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
-                    umma_bf16_ss(tmem_base, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
-                umma_commit(empty_bar(s));
+                    for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
+                        umma_bf16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tfull_bar(acc));
             }
-            umma_commit(tmem_full_bar);
         }
     } else {
         // ---------------------------------------------------- epilogue: 4 warps, one TMEM lane quadrant each
@@ -262,106 +298,178 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tile_kernel(const __grid_co
         const int w = row % p.w_box;
         const int h = (row / p.w_box) % p.h_box;
         const int bb = row / (p.w_box * p.h_box);
-        const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
-        const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
-        mbar_wait(tmem_full_bar, 0, 3);
-        tc_fence_after();
+        // origin of this warp's 32-row sub-box inside the tile (rows q*32 .. q*32+31)
+        const int sw = (q * 32) % p.w_box;
+        const int sh = ((q * 32) / p.w_box) % p.h_box;
+        const int sb = (q * 32) / (p.w_box * p.h_box);
+        const uint32_t out_smem = epi_base + q * GEMM_EPI_WARP_BYTES;       // 2 x 4 KB
+        const uint32_t res_smem = out_smem + 8192;                          // 2 x 4 KB
+        uint8_t* res_ptr = base_ptr + stages * STAGE_BYTES + q * GEMM_EPI_WARP_BYTES + 8192;
+        uint8_t* out_ptr = base_ptr + stages * STAGE_BYTES + q * GEMM_EPI_WARP_BYTES;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-        if constexpr (BLOCK_N == 16) {
-            uint32_t v[16];
-            tmem_ld_32x16(t_lane, v);
-            tmem_ld_wait();
-            if (row_ok) {
-                float eps[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int c = 0; c < p.post.C; ++c) eps[c] = __uint_as_float(v[c]) + __ldg(&p.bias[c]);
-                final_epilogue(p, eps, img, oh, ow);
+        const bool use_res_tma = p.tma_epi && p.resid != nullptr;
+        const bool use_out_tma = p.tma_epi && p.out_f32 != nullptr;
+        uint32_t res_phase = 0;        // bit b = parity of res_bar(q, b)
+        uint32_t out_count = 0;        // output chunks staged so far (buffer = out_count & 1)
+        uint32_t res_count = 0;        // residual chunks requested so far
+        int ti = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+            int w0, h0, b0, n0, z;
+            decode(tile, w0, h0, b0, n0, z);
+            const int acc = ti & 1;
+            const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
+            const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
+            const int c4 = p.epi_c4_is_z ? z : (b0 + sb);
+            if (use_res_tma && lane == 0) {            // residual chunk 0 of this tile: overlaps the main loop
+                const uint32_t b = res_count & 1;
+                mbar_arrive_expect_tx(res_bar(q, b), 4096);
+                tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0, w0 + sw, 0, h0 + sh, c4);
             }
-        } else {
-            const float* bias2 = p.bias2 ? p.bias2 + static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride : nullptr;
-            const long long ro = p.resid ? out_index(p.rs, z, img, oh, ow) : 0;
-            const long long oo = p.out_f32 ? out_index(p.os, z, img, oh, ow) : 0;
-            const long long ho = p.out_bf16 ? out_index(p.hs, z, img, oh, ow) : 0;
-#pragma unroll 1
-            for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
-                uint32_t v[32];
-                tmem_ld_32x32(t_lane + ch * 32, v);
+            mbar_wait(tfull_bar(acc), (ti >> 1) & 1, 3);
+            tc_fence_after();
+            const uint32_t t_acc = t_lane + acc * ACC_COLS;
+
+            if constexpr (BLOCK_N == 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(t_acc, v);
                 tmem_ld_wait();
-                const int nb = n0 + ch * 32;
-                float f[32];
-                const bool full = (nb + 32 <= p.n_valid);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(v[j]) * p.scale;
-                    if (full || nb + j < p.n_valid) {
-                        if (p.bias) x += __ldg(&p.bias[nb + j]);
-                        if (bias2) x += __ldg(&bias2[nb + j]);
-                    } else {
-                        x = 0.f;
-                    }
-                    f[j] = x;
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                if (row_ok) {
+                    float eps[4] = {0.f, 0.f, 0.f, 0.f};
+                    for (int c = 0; c < p.post.C; ++c) eps[c] = __uint_as_float(v[c]) + __ldg(&p.bias[c]);
+                    final_epilogue(p, eps, img, oh, ow);
                 }
-                if (row_ok && p.resid) {
-                    if (full) {
-                        const float4* r4 = reinterpret_cast<const float4*>(p.resid + ro + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 r = __ldg(&r4[j]);
-                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+            } else {
+                const float* bias2 = p.bias2 ? p.bias2 + static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride : nullptr;
+                const long long ro = (p.resid && !use_res_tma) ? out_index(p.rs, z, img, oh, ow) : 0;
+                const long long oo = (p.out_f32 && !use_out_tma) ? out_index(p.os, z, img, oh, ow) : 0;
+                const long long ho = p.out_bf16 ? out_index(p.hs, z, img, oh, ow) : 0;
+                constexpr int NCH = BLOCK_N / 32;
+#pragma unroll 1
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (use_res_tma) {
+                        ++res_count;                         // chunk ch was requested as number res_count
+                        if (ch + 1 < NCH && lane == 0) {     // request the next chunk into the other buffer (freed one chunk ago)
+                            const uint32_t b = res_count & 1;
+                            mbar_arrive_expect_tx(res_bar(q, b), 4096);
+                            tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0 + (ch + 1) * 32, w0 + sw, 0, h0 + sh, c4);
                         }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
                     }
-                }
-                if (row_ok && p.out_f32) {
-                    if (full) {
-                        float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + ch * 32, v);
+                    tmem_ld_wait();
+                    if (ch == NCH - 1) {                     // accumulator fully read: hand it back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
                     }
-                }
-                if (row_ok && p.out_bf16) {
-                    if (full) {
-                        uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            __nv_bfloat162 h0v = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-                            __nv_bfloat162 h1v = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-                            __nv_bfloat162 h2v = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-                            __nv_bfloat162 h3v = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-                            uint4 u;
-                            u.x = *reinterpret_cast<uint32_t*>(&h0v); u.y = *reinterpret_cast<uint32_t*>(&h1v);
-                            u.z = *reinterpret_cast<uint32_t*>(&h2v); u.w = *reinterpret_cast<uint32_t*>(&h3v);
-                            o4[j] = u;
-                        }
-                    } else {
-                        for (int j = 0; j < 32; ++j)
-                            if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
-                    }
-                }
-                if (p.stats) {
-                    // every row of this warp belongs to the same image (w_box*h_box is a multiple of 32)
-                    float s1[32], s2[32];
+                    const int nb = n0 + ch * 32;
+                    float f[32];
+                    const bool full = (nb + 32 <= p.n_valid);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const float x = row_ok ? f[j] : 0.f;
-                        s1[j] = x; s2[j] = x * x;
+                        float x = __uint_as_float(v[j]) * p.scale;
+                        if (full || nb + j < p.n_valid) {
+                            if (p.bias) x += __ldg(&p.bias[nb + j]);
+                            if (bias2) x += __ldg(&bias2[nb + j]);
+                        } else {
+                            x = 0.f;
+                        }
+                        f[j] = x;
                     }
-                    const float cs = warp_column_sums(s1);
-                    const float cq = warp_column_sums(s2);
-                    const int img0 = __shfl_sync(0xffffffffu, img, 0);
-                    if (img0 < p.OB && nb + lane < p.n_valid) {
-                        float* st = p.stats + (static_cast<long long>(img0) * p.stats_C + p.stats_coff + nb + lane) * 2;
-                        atomicAdd(st, cs);
-                        atomicAdd(st + 1, cq);
+                    if (use_res_tma) {
+                        const uint32_t b = (res_count - 1) & 1;
+                        mbar_wait(res_bar(q, b), (res_phase >> b) & 1u, 5);
+                        res_phase ^= (1u << b);
+                        const uint8_t* rp = res_ptr + b * 4096 + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 r = *reinterpret_cast<const float4*>(rp + ((j ^ (lane & 7)) << 4));
+                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                        }
+                        __syncwarp();                        // everyone is done with this buffer before it is re-requested
+                    } else if (row_ok && p.resid) {
+                        if (full) {
+                            const float4* r4 = reinterpret_cast<const float4*>(p.resid + ro + nb);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 r = __ldg(&r4[j]);
+                                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
+                        }
+                    }
+                    if (use_out_tma) {
+                        const uint32_t b = out_count & 1;
+                        if (out_count >= 2) {                // the store issued two chunks ago must have finished reading smem
+                            if (lane == 0) tma_store_wait_read<1>();
+                            __syncwarp();
+                        }
+                        uint8_t* op = out_ptr + b * 4096 + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(op + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_5d(&p.out_map, out_smem + b * 4096, nb, w0 + sw, 0, h0 + sh, c4);
+                            tma_store_commit();
+                        }
+                        ++out_count;
+                    } else if (row_ok && p.out_f32) {
+                        if (full) {
+                            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
+                        }
+                    }
+                    if (row_ok && p.out_bf16) {
+                        if (full) {
+                            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 h0v = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                                __nv_bfloat162 h1v = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                                __nv_bfloat162 h2v = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                                __nv_bfloat162 h3v = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                                uint4 u;
+                                u.x = *reinterpret_cast<uint32_t*>(&h0v); u.y = *reinterpret_cast<uint32_t*>(&h1v);
+                                u.z = *reinterpret_cast<uint32_t*>(&h2v); u.w = *reinterpret_cast<uint32_t*>(&h3v);
+                                o4[j] = u;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
+                        }
+                    }
+                    if (p.stats) {
+                        // every row of this warp belongs to the same image (w_box*h_box is a multiple of 32)
+                        float s1[32], s2[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = row_ok ? f[j] : 0.f;
+                            s1[j] = x; s2[j] = x * x;
+                        }
+                        const float cs = warp_column_sums(s1);
+                        const float cq = warp_column_sums(s2);
+                        const int img0 = __shfl_sync(0xffffffffu, img, 0);
+                        if (img0 < p.OB && nb + lane < p.n_valid) {
+                            float* st = p.stats + (static_cast<long long>(img0) * p.stats_C + p.stats_coff + nb + lane) * 2;
+                            atomicAdd(st, cs);
+                            atomicAdd(st + 1, cq);
+                        }
                     }
                 }
             }
         }
+        if (use_out_tma && lane == 0) tma_store_wait_all<0>();      // smem must outlive the last bulk stores
     }
     tc_fence_before();
     __syncthreads();
