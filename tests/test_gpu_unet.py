@@ -169,7 +169,7 @@ def test_state_dict_roundtrip_and_reload():
     e1 = net.denoise_fn(x, nl)
     net2 = build(TINY_UNET, 32, 2)
     e2 = net2.denoise_fn(x, nl)
-    assert rel(e2, e1) > 1e-2
+    assert rel(e2, e1) > 0.1
     net2.load_state_dict(sd, strict=True)
     e3 = net2.denoise_fn(x, nl)
-    assert rel(e3, e1) < 1e-4
+    assert rel(e3, e1) < BF16_TOL      # not bit-identical: atomic-order noise in the GN sums flips bf16 roundings (~5e-3)
