@@ -46,6 +46,7 @@ _SIGS = {
     "sr3_engine_num_launches_per_step": (c_int, [c_void_p]),
     "sr3_engine_workspace_bytes": (c_int64, [c_void_p]),
     "sr3_engine_read_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int), c_void_p]),
+    "sr3_bench_conv": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "sr3_test_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sr3_test_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
@@ -260,6 +261,12 @@ class Engine:
         t = torch.empty(tuple(shape), device=self.device, dtype=torch.float32)
         _check(lib().sr3_engine_read_activation(self._h, name.encode(), _ptr(t), t.numel(), ctypes.byref(numel), shape, _stream()))
         return t.permute(0, 3, 1, 2).contiguous()
+
+
+def bench_conv(B, H, W, Cin, Cout, k=3, stride=1, resid=False, stats=True, reps=20):
+    ms = c_float()
+    _check(lib().sr3_bench_conv(B, H, W, Cin, Cout, k, stride, int(resid), int(stats), reps, ctypes.byref(ms)))
+    return ms.value
 
 
 def test_gemm(a_bf16, b_bf16, block_n):

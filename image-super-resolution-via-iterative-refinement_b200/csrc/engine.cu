@@ -181,7 +181,7 @@ typedef std::function<void(cudaStream_t)> Op;
 // Turns a GemmDesc into a launchable op (encodes the TMA maps, uploads the K-slab table).
 Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     REQUIRE(d.w_box * d.h_box * d.b_box == 128, "tile box must cover 128 rows");
-    REQUIRE(!d.slabs.empty(), "gemm without K slabs");
+    REQUIRE(!d.slabs.empty() && (int)d.slabs.size() <= GEMM_MAX_K, "gemm with %d K slabs (max %d)", (int)d.slabs.size(), GEMM_MAX_K);
     GemmParams p;
     memset(&p, 0, sizeof(p));
     for (int i = 0; i < 2; ++i) {
@@ -213,6 +213,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
     p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
     p.stages = pick_stages(d.block_n);
+    p.dbg = getenv("SR3_DBG") ? atoi(getenv("SR3_DBG")) : 0;
     p.n_tiles = d.n_tiles; p.nz = d.nz;
     p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
     p.bias = d.bias; p.bias2 = d.bias2; p.bias2_stride = d.bias2_stride;
@@ -1098,6 +1099,44 @@ int sr3_test_gemm(const void* a, const void* b, float* dptr, int M, int N, int K
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     op(st);
     CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int with_resid, int with_stats, int reps, float* ms_out) {
+    API_BEGIN
+    REQUIRE(ms_out && reps > 0, "bad arguments");
+    DevAllocs mem;
+    const int ktot = ksize * ksize * Cin;
+    const int OH = H / stride, OW = W / stride;
+    bf16* x = static_cast<bf16*>(mem.alloc((size_t)B * H * W * Cin * 2));
+    bf16* wp = static_cast<bf16*>(mem.alloc((size_t)Cout * ktot * 2));
+    float* y = static_cast<float*>(mem.alloc((size_t)B * OH * OW * Cout * 4));
+    float* r = with_resid ? static_cast<float*>(mem.alloc((size_t)B * OH * OW * Cout * 4)) : nullptr;
+    float* st = with_stats ? static_cast<float*>(mem.alloc((size_t)B * Cout * 2 * 4)) : nullptr;
+    float* bias = static_cast<float*>(mem.alloc((size_t)Cout * 4));
+    GemmDesc d; d.n_a = 1;
+    d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
+    add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
+    d.block_n = pick_block_n(Cout); d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
+    pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
+    REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
+    d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = B / d.b_box; d.n_tiles = Cout / d.block_n;
+    d.OW = OW; d.OH = OH; d.OB = B; d.n_valid = Cout; d.bias = bias;
+    d.out_f32 = y; d.os = nhwc_out(OH, OW, Cout);
+    d.resid = r; d.rs = nhwc_out(OH, OW, Cout);
+    d.stats = st; d.stats_C = Cout;
+    Op op = make_gemm_op(d, mem);
+    cudaStream_t s0 = nullptr;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) op(s0);
+    CK(cudaEventRecord(e0, s0));
+    for (int i = 0; i < reps; ++i) op(s0);
+    CK(cudaEventRecord(e1, s0));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
     API_END
 }
 

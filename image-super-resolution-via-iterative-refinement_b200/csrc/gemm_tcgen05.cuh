@@ -59,9 +59,11 @@ struct GemmParams {
     const int4* ktab;        // [num_k] {a_sel, a_chan, dw | dh<<8 | p<<16, b_col}
     int num_k;
     int tiles_w, tiles_h, tiles_b;
-    int n_tiles, nz;         // persistent schedule: tile = n_tile + n_tiles * (m_tile + tiles_m * z)
+    int n_tiles, nz;         // persistent schedule: tile = m_tile + tiles_m * (n_tile + n_tiles * z); CTA c owns a contiguous range
     int tma_epi;             // 1: fp32 output / residual go through smem + TMA (out_map / res_map)
     int epi_c4_is_z;         // 5th coordinate of out_map / res_map: gemm-batch z (1) or image index (0)
+    int dbg;                 // SR3_DBG bit mask (timing experiments only): 1 skip epilogue body, 2 skip stats, 4 skip out store,
+                             // 8 skip A loads, 16 skip B loads, 32 skip MMAs
     int w_box, h_box, b_box;
     int a_zstep, b_zrows;
     int stages;
@@ -89,10 +91,12 @@ constexpr int GEMM_MAX_STAGES = 8;
 constexpr int GEMM_A_BYTES = 128 * 128;
 constexpr int GEMM_EPI_WARP_BYTES = 16384;   // per epilogue warp: 2 x 4 KB output staging + 2 x 4 KB residual staging
 constexpr int GEMM_EPI_BYTES = 4 * GEMM_EPI_WARP_BYTES;
+constexpr int GEMM_MAX_K = 192;              // K slabs per tile (3x3 conv over 1024 channels + 1x1 residual conv over 1024 = 160)
+constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 16 /*K-slab table*/ + 4 * 2 * 32 * 4 /*per-warp bias staging*/;
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n) { return GEMM_A_BYTES + block_n * 128; }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
-    return stages * gemm_stage_bytes(block_n) + GEMM_EPI_BYTES + 1024 /*align slack*/ + 512 /*barriers*/;
+    return stages * gemm_stage_bytes(block_n) + GEMM_EPI_BYTES + 1024 /*align slack*/ + GEMM_AUX_BYTES;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
@@ -203,10 +207,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     volatile uint32_t* tmem_slot =
         reinterpret_cast<volatile uint32_t*>(base_ptr + stages * STAGE_BYTES + GEMM_EPI_BYTES + 8 * (2 * GEMM_MAX_STAGES + 12));
 
+    // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
+    int4* ktab_s = reinterpret_cast<int4*>(base_ptr + stages * STAGE_BYTES + GEMM_EPI_BYTES + 512);
+    float* bias_s = reinterpret_cast<float*>(base_ptr + stages * STAGE_BYTES + GEMM_EPI_BYTES + 512 + GEMM_MAX_K * 16);
+
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     const int total_tiles = tiles_m * p.n_tiles * p.nz;
+    for (int k = threadIdx.x; k < p.num_k; k += GEMM_THREADS) ktab_s[k] = __ldg(&p.ktab[k]);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.a_map[0]);
@@ -234,61 +243,73 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     const uint32_t tmem_base = *tmem_slot;
 
     auto decode = [&](int tile, int& w0, int& h0, int& b0, int& n0, int& z) {
-        const int nt = tile % p.n_tiles;
-        const int r = tile / p.n_tiles;
-        const int tm = r % tiles_m;
-        z = r / tiles_m;
+        const int tm = tile % tiles_m;          // m fastest: a CTA's consecutive tiles share the weight slab and mostly the image
+        const int r = tile / tiles_m;
+        const int nt = r % p.n_tiles;
+        z = r / p.n_tiles;
         const int tw = tm % p.tiles_w;
         const int th = (tm / p.tiles_w) % p.tiles_h;
         const int tb = tm / (p.tiles_w * p.tiles_h);
         w0 = tw * p.w_box; h0 = th * p.h_box; b0 = tb * p.b_box + z * p.a_zstep; n0 = nt * BLOCK_N;
     };
 
+    // contiguous tile range of this CTA (balanced to +-1 tile)
+    const int tile_begin = static_cast<int>((static_cast<long long>(total_tiles) * blockIdx.x) / gridDim.x);
+    const int tile_end = static_cast<int>((static_cast<long long>(total_tiles) * (blockIdx.x + 1)) / gridDim.x);
+
     if (warp == 0) {
-        if (lane == 0) {
-            // ------------------------------------------------ TMA producer (runs ahead across tiles)
-            int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                int w0, h0, b0, n0, z;
-                decode(tile, w0, h0, b0, n0, z);
-                for (int k = 0; k < p.num_k; ++k, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(empty_bar(s), ph ^ 1u, 1);
-                    const int4 e = __ldg(&p.ktab[k]);
+        // ---------------------------------------------------- TMA producer warp (converged; one elected lane issues)
+        int s = 0;
+        uint32_t ph = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile) {
+            int w0, h0, b0, n0, z;
+            decode(tile, w0, h0, b0, n0, z);
+            const int brow = n0 + z * p.b_zrows;
+            for (int k = 0; k < p.num_k; ++k) {
+                mbar_wait(empty_bar(s), ph ^ 1u, 1);
+                if (elect_one_sync()) {
+                    const int4 e = ktab_s[k];
                     const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
                     const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
                     const int pp = (e.z >> 16) & 0xff;
                     const uint32_t a_dst = base + s * STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar(s), STAGE_BYTES);
-                    tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
-                    tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, n0 + z * p.b_zrows);
+                    mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : GEMM_A_BYTES) + ((p.dbg & 16) ? 0 : B_BYTES));
+                    if (!(p.dbg & 8)) tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
+                    if (!(p.dbg & 16)) tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, brow);
                 }
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ------------------------------------------------ MMA issuer (one thread)
-            int it = 0, ti = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
-                const int acc = ti & 1;
-                mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
+        // ---------------------------------------------------- MMA issuer warp (converged; one elected lane issues)
+        // descriptor low words: start address field advances by STAGE_BYTES/16 per stage, +2 per UMMA_K step
+        const uint64_t desc_hi = umma_desc_kmajor_sw128(0, 1024) & 0xFFFFFFFF00000000ull;
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_kmajor_sw128(base, 1024) & 0xFFFFFFFFull);
+        int s = 0, ti = 0;
+        uint32_t ph = 0;
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++ti) {
+            const int acc = ti & 1;
+            mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            for (int k = 0; k < p.num_k; ++k) {
+                mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-                for (int k = 0; k < p.num_k; ++k, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(full_bar(s), ph, 2);
-                    tc_fence_after();
-                    const uint32_t a_addr = base + s * STAGE_BYTES;
-                    const uint64_t adesc = umma_desc_kmajor_sw128(a_addr, 1024);
-                    const uint64_t bdesc = umma_desc_kmajor_sw128(a_addr + GEMM_A_BYTES, 1024);
+                if (elect_one_sync()) {
+                    const uint32_t alo = desc_lo0 + s * (STAGE_BYTES >> 4);
+                    const uint64_t adesc = desc_hi | alo;
+                    const uint64_t bdesc = desc_hi | (alo + (GEMM_A_BYTES >> 4));
+                    if (!(p.dbg & 32)) {
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
-                        umma_bf16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
+                        for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
+                            umma_bf16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
+                    }
                     umma_commit(empty_bar(s));
+                    if (k == p.num_k - 1) umma_commit(tfull_bar(acc));
                 }
-                umma_commit(tfull_bar(acc));
+                __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
     } else {
@@ -312,12 +333,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         uint32_t res_phase = 0;        // bit b = parity of res_bar(q, b)
         uint32_t out_count = 0;        // output chunks staged so far (buffer = out_count & 1)
         uint32_t res_count = 0;        // residual chunks requested so far
+        // GroupNorm partial sums of this lane's column, kept in registers across tiles of the same (image, column block)
+        constexpr int NCHS = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;
+        float st_sum[NCHS], st_sq[NCHS];
+#pragma unroll
+        for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        int st_img = -1, st_n0 = -1;
+        auto flush_stats = [&]() {
+            if (st_img >= 0 && st_img < p.OB) {
+#pragma unroll
+                for (int c = 0; c < NCHS; ++c) {
+                    const int n = st_n0 + c * 32 + lane;
+                    if (n < p.n_valid) {
+                        float* st = p.stats + (static_cast<long long>(st_img) * p.stats_C + p.stats_coff + n) * 2;
+                        atomicAdd(st, st_sum[c]);
+                        atomicAdd(st + 1, st_sq[c]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        };
         int ti = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        for (int tile = tile_begin; tile < tile_end; ++tile, ++ti) {
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int acc = ti & 1;
             const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
+            if (p.stats && !(p.dbg & 2)) {
+                const int img0 = __shfl_sync(0xffffffffu, img, 0);      // all rows of a warp belong to one image
+                if (img0 != st_img || n0 != st_n0) { flush_stats(); st_img = img0; st_n0 = n0; }
+            }
             const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
             const int c4 = p.epi_c4_is_z ? z : (b0 + sb);
             if (use_res_tma && lane == 0) {            // residual chunk 0 of this tile: overlaps the main loop
@@ -347,8 +393,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 const long long oo = (p.out_f32 && !use_out_tma) ? out_index(p.os, z, img, oh, ow) : 0;
                 const long long ho = p.out_bf16 ? out_index(p.hs, z, img, oh, ow) : 0;
                 constexpr int NCH = BLOCK_N / 32;
+                // bias (+ per-image FiLM bias) of this lane's column, fetched one chunk ahead, broadcast through smem
+                auto load_bias = [&](int nbq) -> float {
+                    float v = 0.f;
+                    if (nbq + lane < p.n_valid) {
+                        if (p.bias) v += __ldg(&p.bias[nbq + lane]);
+                        if (bias2) v += __ldg(&bias2[nbq + lane]);
+                    }
+                    return v;
+                };
+                float bnext = load_bias(n0);
 #pragma unroll 1
                 for (int ch = 0; ch < NCH; ++ch) {
+                    float* bs = bias_s + (q * 2 + (ch & 1)) * 32;
+                    bs[lane] = bnext;
+                    if (ch + 1 < NCH) bnext = load_bias(n0 + (ch + 1) * 32);
+                    __syncwarp();
                     if (use_res_tma) {
                         ++res_count;                         // chunk ch was requested as number res_count
                         if (ch + 1 < NCH && lane == 0) {     // request the next chunk into the other buffer (freed one chunk ago)
@@ -365,18 +425,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(acc));
                     }
+                    if (p.dbg & 1) continue;
                     const int nb = n0 + ch * 32;
                     float f[32];
                     const bool full = (nb + 32 <= p.n_valid);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]) * p.scale;
-                        if (full || nb + j < p.n_valid) {
-                            if (p.bias) x += __ldg(&p.bias[nb + j]);
-                            if (bias2) x += __ldg(&bias2[nb + j]);
-                        } else {
-                            x = 0.f;
-                        }
+                        float x = __uint_as_float(v[j]) * p.scale + bs[j];
+                        if (!full && nb + j >= p.n_valid) x = 0.f;
                         f[j] = x;
                     }
                     if (use_res_tma) {
@@ -403,7 +459,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
                         }
                     }
-                    if (use_out_tma) {
+                    if (p.dbg & 4) {
+                    } else if (use_out_tma) {
                         const uint32_t b = out_count & 1;
                         if (out_count >= 2) {                // the store issued two chunks ago must have finished reading smem
                             if (lane == 0) tma_store_wait_read<1>();
@@ -449,8 +506,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
                         }
                     }
-                    if (p.stats) {
-                        // every row of this warp belongs to the same image (w_box*h_box is a multiple of 32)
+                    if (p.stats && !(p.dbg & 2)) {
                         float s1[32], s2[32];
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
@@ -459,16 +515,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         }
                         const float cs = warp_column_sums(s1);
                         const float cq = warp_column_sums(s2);
-                        const int img0 = __shfl_sync(0xffffffffu, img, 0);
-                        if (img0 < p.OB && nb + lane < p.n_valid) {
-                            float* st = p.stats + (static_cast<long long>(img0) * p.stats_C + p.stats_coff + nb + lane) * 2;
-                            atomicAdd(st, cs);
-                            atomicAdd(st + 1, cq);
-                        }
+#pragma unroll
+                        for (int c = 0; c < NCHS; ++c)
+                            if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
                     }
                 }
             }
         }
+        if (p.stats && !(p.dbg & 2)) flush_stats();
         if (use_out_tma && lane == 0) tma_store_wait_all<0>();      // smem must outlive the last bulk stores
     }
     tc_fence_before();

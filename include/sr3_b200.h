@@ -116,6 +116,9 @@ int sr3_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N
 int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin,
                   int Cout, int ksize, int stride, void* stream);
 
+/* Timing harness for one conv shape on zero-filled buffers (kernel-tuning experiments): average ms over `reps` launches. */
+int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int with_resid, int with_stats, int reps, float* ms_out);
+
 #ifdef __cplusplus
 }
 #endif
