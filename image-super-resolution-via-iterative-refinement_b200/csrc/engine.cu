@@ -128,11 +128,17 @@ OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
 }
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
+int pick_kps(int block_n) {
+    if (block_n >= 256) return 1;
+    if (block_n == 128) { const char* e = getenv("SR3_KPS128"); return e ? atoi(e) : 1; }
+    const char* e = getenv("SR3_KPS64");
+    return e ? atoi(e) : 2;
+}
 int pick_stages(int block_n) {
     int s = GEMM_MAX_STAGES;
     if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    while (s > 1 && gemm_smem_bytes(block_n, s) > SMEM_LIMIT) --s;
+    while (s > 1 && gemm_smem_bytes(block_n, pick_kps(block_n), s) > SMEM_LIMIT) --s;
     if (s < 1) s = 1;
     return s;
 }
@@ -146,18 +152,20 @@ int num_sms() {
     return n;
 }
 
-template <int BN>
+template <int BN, int KPS>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
-    gemm_tile_kernel<BN><<<grid, GEMM_THREADS, smem, st>>>(p);
+    gemm_tile_kernel<BN, KPS><<<grid, GEMM_THREADS, smem, st>>>(p);
     CK(cudaGetLastError());
 }
 void init_gemm_attrs() {
     static bool done = false;
     if (done) return;
-    CK(cudaFuncSetAttribute(gemm_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    CK(cudaFuncSetAttribute(gemm_tile_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    CK(cudaFuncSetAttribute(gemm_tile_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    CK(cudaFuncSetAttribute(gemm_tile_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     done = true;
 }
 
@@ -254,16 +262,17 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     if (const char* e = getenv("SR3_MAX_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }
     const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
-    const int smem = gemm_smem_bytes(bn, p.stages);
+    const int kps = pick_kps(bn);
+    const int smem = gemm_smem_bytes(bn, kps, p.stages);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
     REQUIRE(bn == 16 || bn == 64 || bn == 128 || bn == 256, "unsupported block_n %d", bn);
-    return [p, grid, bn, smem](cudaStream_t st) {
+    return [p, grid, bn, kps, smem](cudaStream_t st) {
         switch (bn) {
-            case 16: launch_gemm_bn<16>(p, grid, smem, st); break;
-            case 64: launch_gemm_bn<64>(p, grid, smem, st); break;
-            case 128: launch_gemm_bn<128>(p, grid, smem, st); break;
-            default: launch_gemm_bn<256>(p, grid, smem, st); break;
+            case 16: launch_gemm_bn<16, 2>(p, grid, smem, st); break;
+            case 64: if (kps == 2) launch_gemm_bn<64, 2>(p, grid, smem, st); else launch_gemm_bn<64, 1>(p, grid, smem, st); break;
+            case 128: if (kps == 2) launch_gemm_bn<128, 2>(p, grid, smem, st); else launch_gemm_bn<128, 1>(p, grid, smem, st); break;
+            default: launch_gemm_bn<256, 1>(p, grid, smem, st); break;
         }
     };
 }
@@ -444,7 +453,9 @@ struct sr3_engine {
         p.out_a = out_a; p.out_raw = out_raw;
         const int C = p.C0 + p.C1;
         REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
-        int ppb = 4096 / C; if (ppb < 1) ppb = 1; if (ppb > p.HW) ppb = p.HW;
+        int ppb = 32768 / C;                                   // ~32 float4 per thread amortise the per-block statistics prologue
+        { const int cap = (int)(((long long)p.HW * B) / 296); if (ppb > cap) ppb = cap; }   // but keep >= 2 blocks per SM when possible
+        if (ppb < 1) ppb = 1; if (ppb > p.HW) ppb = p.HW;
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);

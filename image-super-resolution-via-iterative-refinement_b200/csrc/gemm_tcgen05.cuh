@@ -94,9 +94,10 @@ constexpr int GEMM_EPI_BYTES = 4 * GEMM_EPI_WARP_BYTES;
 constexpr int GEMM_MAX_K = 192;              // K slabs per tile (3x3 conv over 1024 channels + 1x1 residual conv over 1024 = 160)
 constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 16 /*K-slab table*/ + 4 * 2 * 32 * 4 /*per-warp bias staging*/;
 
-__host__ __device__ constexpr int gemm_stage_bytes(int block_n) { return GEMM_A_BYTES + block_n * 128; }
-__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int stages) {
-    return stages * gemm_stage_bytes(block_n) + GEMM_EPI_BYTES + 1024 /*align slack*/ + GEMM_AUX_BYTES;
+// kps = K slabs (64 channels each) per pipeline stage: 2 halves the mbarrier handshakes per MMA at the cost of pipeline depth
+__host__ __device__ constexpr int gemm_stage_bytes(int block_n, int kps) { return kps * (GEMM_A_BYTES + block_n * 128); }
+__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int kps, int stages) {
+    return stages * gemm_stage_bytes(block_n, kps) + GEMM_EPI_BYTES + 1024 /*align slack*/ + GEMM_AUX_BYTES;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
@@ -183,10 +184,11 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
 
 // Persistent, warp-specialised tile kernel.  Each CTA walks tiles blockIdx.x, +gridDim.x, ...; the accumulator is double
 // buffered in TMEM so the epilogue of tile i overlaps the MMAs of tile i+1, and the TMA producer runs ahead across tiles.
-template <int BLOCK_N>
+template <int BLOCK_N, int GEMM_KPS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
     constexpr int B_BYTES = BLOCK_N * 128;
-    constexpr int STAGE_BYTES = GEMM_A_BYTES + B_BYTES;
+    constexpr int SLAB_BYTES = GEMM_A_BYTES + B_BYTES;                      // one 64-channel K slab: A tile then B tile
+    constexpr int STAGE_BYTES = GEMM_KPS * SLAB_BYTES;
     constexpr uint32_t ACC_COLS = BLOCK_N;                                  // columns per accumulator buffer
     constexpr uint32_t TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;   // two buffers, power of two >= 32
     constexpr uint32_t IDESC = umma_idesc_bf16(128, BLOCK_N);
@@ -265,17 +267,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int brow = n0 + z * p.b_zrows;
-            for (int k = 0; k < p.num_k; ++k) {
+            for (int k = 0; k < p.num_k; k += GEMM_KPS) {
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
-                    const int4 e = ktab_s[k];
-                    const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
-                    const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
-                    const int pp = (e.z >> 16) & 0xff;
-                    const uint32_t a_dst = base + s * STAGE_BYTES;
-                    mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : GEMM_A_BYTES) + ((p.dbg & 16) ? 0 : B_BYTES));
-                    if (!(p.dbg & 8)) tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
-                    if (!(p.dbg & 16)) tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, brow);
+                    const int nslab = (p.num_k - k) < GEMM_KPS ? (p.num_k - k) : GEMM_KPS;
+                    mbar_arrive_expect_tx(full_bar(s), nslab * (((p.dbg & 8) ? 0 : GEMM_A_BYTES) + ((p.dbg & 16) ? 0 : B_BYTES)));
+#pragma unroll
+                    for (int j = 0; j < GEMM_KPS; ++j) {
+                        if (j < nslab) {
+                            const int4 e = ktab_s[k + j];
+                            const int dw = static_cast<int>(static_cast<int8_t>(e.z & 0xff));
+                            const int dh = static_cast<int>(static_cast<int8_t>((e.z >> 8) & 0xff));
+                            const int pp = (e.z >> 16) & 0xff;
+                            const uint32_t a_dst = base + s * STAGE_BYTES + j * SLAB_BYTES;
+                            if (!(p.dbg & 8)) tma_load_5d(a_dst, &p.a_map[e.x], full_bar(s), e.y, w0 + dw, pp, h0 + dh, b0);
+                            if (!(p.dbg & 16)) tma_load_2d(a_dst + GEMM_A_BYTES, &p.b_map, full_bar(s), e.w, brow);
+                        }
+                    }
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -293,20 +301,26 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int k = 0; k < p.num_k; ++k) {
+            for (int k = 0; k < p.num_k; k += GEMM_KPS) {
                 mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t alo = desc_lo0 + s * (STAGE_BYTES >> 4);
-                    const uint64_t adesc = desc_hi | alo;
-                    const uint64_t bdesc = desc_hi | (alo + (GEMM_A_BYTES >> 4));
+                    const int nslab = (p.num_k - k) < GEMM_KPS ? (p.num_k - k) : GEMM_KPS;
                     if (!(p.dbg & 32)) {
 #pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
-                            umma_bf16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | kk) != 0);
+                        for (int j = 0; j < GEMM_KPS; ++j) {
+                            if (j < nslab) {
+                                const uint32_t alo = desc_lo0 + (s * STAGE_BYTES + j * SLAB_BYTES) / 16;
+                                const uint64_t adesc = desc_hi | alo;
+                                const uint64_t bdesc = desc_hi | (alo + (GEMM_A_BYTES >> 4));
+#pragma unroll
+                                for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
+                                    umma_bf16_ss(d_tmem, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | j | kk) != 0);
+                            }
+                        }
                     }
                     umma_commit(empty_bar(s));
-                    if (k == p.num_k - 1) umma_commit(tfull_bar(acc));
+                    if (k + GEMM_KPS >= p.num_k) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
