@@ -109,7 +109,11 @@ struct GemmDesc {
     long long b_rows = 0; int b_K = 0;            // B matrix [b_rows][b_K] bf16 row-major
     std::vector<KSlab> slabs;
     int block_n = 128;
-    int w_box = 16, h_box = 8, b_box = 1;
+    int w_box = 16, h_box = 8, b_box = 1;         // output pixel patch of one tile (mh * 128 rows)
+    int mh = 1;                                   // 128-row accumulator halves per tile
+    int tall = 0;                                 // 3x3 stride-1 "tall halo" mode: A box = 8 x (rows + 2) pixels, vertical taps share it
+    int a_box_w = 0, a_box_h = 0, a_box_b = 0;    // TMA box of the A operand (0: same as the tile patch)
+    int a_half_off = 0;
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
     // epilogue
@@ -128,17 +132,11 @@ OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
 }
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
-int pick_kps(int block_n) {
-    if (block_n >= 256) return 1;
-    if (block_n == 128) { const char* e = getenv("SR3_KPS128"); return e ? atoi(e) : 1; }
-    const char* e = getenv("SR3_KPS64");
-    return e ? atoi(e) : 2;
-}
-int pick_stages(int block_n) {
+int pick_stages(int block_n, int a_stage_bytes, int b_taps) {
     int s = GEMM_MAX_STAGES;
     if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    while (s > 1 && gemm_smem_bytes(block_n, pick_kps(block_n), s) > SMEM_LIMIT) --s;
+    while (s > 1 && gemm_smem_bytes(block_n, a_stage_bytes, b_taps, s) > SMEM_LIMIT) --s;
     if (s < 1) s = 1;
     return s;
 }
@@ -151,15 +149,15 @@ int num_sms() {
     }
     return n;
 }
-
-template <int BN, int KPS>
+template <int BN, int MH>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
-    gemm_tile_kernel<BN, KPS><<<grid, GEMM_THREADS, smem, st>>>(p);
+    gemm_tile_kernel<BN, MH><<<grid, GEMM_THREADS, smem, st>>>(p);
     CK(cudaGetLastError());
 }
 void init_gemm_attrs() {
     static bool done = false;
     if (done) return;
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -188,16 +186,19 @@ typedef std::function<void(cudaStream_t)> Op;
 
 // Turns a GemmDesc into a launchable op (encodes the TMA maps, uploads the K-slab table).
 Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
-    REQUIRE(d.w_box * d.h_box * d.b_box == 128, "tile box must cover 128 rows");
-    REQUIRE(!d.slabs.empty() && (int)d.slabs.size() <= GEMM_MAX_K, "gemm with %d K slabs (max %d)", (int)d.slabs.size(), GEMM_MAX_K);
+    REQUIRE(d.w_box * d.h_box * d.b_box == 128 * d.mh, "tile box must cover %d rows", 128 * d.mh);
+    REQUIRE(!d.slabs.empty(), "gemm without K slabs");
     GemmParams p;
     memset(&p, 0, sizeof(p));
+    const int abw = d.a_box_w ? d.a_box_w : d.w_box, abh = d.a_box_h ? d.a_box_h : d.h_box, abb = d.a_box_b ? d.a_box_b : d.b_box;
+    p.a_stage_bytes = abw * abh * abb * 128;
+    REQUIRE(p.a_stage_bytes % 1024 == 0, "A box must be a whole number of swizzle atoms");
     for (int i = 0; i < 2; ++i) {
         const ASrc& a = d.a[i < d.n_a ? i : 0];
         REQUIRE(a.C % 64 == 0, "A channels (%d) must be a multiple of 64", a.C);
         const uint64_t dims[5] = {(uint64_t)a.C, (uint64_t)a.W, (uint64_t)a.P, (uint64_t)a.H, (uint64_t)a.Bn};
         const uint64_t str[4] = {(uint64_t)a.sW, (uint64_t)a.sP, (uint64_t)a.sH, (uint64_t)a.sB};
-        const uint32_t box[5] = {64u, (uint32_t)d.w_box, 1u, (uint32_t)d.h_box, (uint32_t)d.b_box};
+        const uint32_t box[5] = {64u, (uint32_t)abw, 1u, (uint32_t)abh, (uint32_t)abb};
         p.a_map[i] = encode_map(5, a.ptr, dims, str, box);
     }
     {
@@ -208,19 +209,38 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
         REQUIRE(d.b_rows >= d.block_n, "B rows %lld < block_n %d", d.b_rows, d.block_n);
         p.b_map = encode_map(2, d.b_ptr, dims, str, box);
     }
-    std::vector<int4> tab(d.slabs.size());
+    // stage table: in tall mode the three vertical taps (dh = -1, 0, +1) of one (source, channel chunk, dw) share a stage
+    std::vector<StageDesc> tab;
+    int b_taps = 1;
     for (size_t i = 0; i < d.slabs.size(); ++i) {
-        const KSlab& s = d.slabs[i];
-        REQUIRE(s.a_sel < d.n_a, "slab refers to missing A source");
-        tab[i] = make_int4(s.a_sel, s.a_chan, (s.dw & 0xff) | ((s.dh & 0xff) << 8) | ((s.p & 0xff) << 16), s.b_col);
+        const KSlab& k = d.slabs[i];
+        REQUIRE(k.a_sel < d.n_a, "slab refers to missing A source");
+        StageDesc e; memset(&e, 0, sizeof(e));
+        e.a_sel = k.a_sel; e.a_chan = k.a_chan; e.dw = k.dw; e.dh = k.dh; e.p = k.p; e.ntaps = 1; e.b_col0 = k.b_col;
+        if (d.tall) {
+            REQUIRE(k.p == 0 && k.dh >= -1 && k.dh <= 1, "tall mode needs stride-1 taps");
+            auto sibling = [&](int dh) -> const KSlab* {
+                for (const KSlab& o : d.slabs) if (o.a_sel == k.a_sel && o.a_chan == k.a_chan && o.dw == k.dw && o.dh == dh) return &o;
+                return nullptr;
+            };
+            const KSlab *s0 = sibling(-1), *s1 = sibling(0), *s2 = sibling(1);
+            const bool grouped = s0 && s1 && s2 && (s2->b_col - s1->b_col == s1->b_col - s0->b_col);
+            if (grouped && k.dh != -1) continue;          // folded into the dh = -1 stage
+            e.dh = -1;                                    // the box always starts one row above the tile
+            if (grouped) { e.ntaps = 3; e.b_col_step = s1->b_col - s0->b_col; e.a_off0 = 0; e.a_off_step = 1024; b_taps = 3; }
+            else { e.a_off0 = (k.dh + 1) * 1024; }
+        }
+        tab.push_back(e);
     }
-    int4* dtab = static_cast<int4*>(mem.alloc(tab.size() * sizeof(int4), false));
-    CK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    REQUIRE((int)tab.size() <= GEMM_MAX_K, "gemm with %d stages per tile (max %d)", (int)tab.size(), GEMM_MAX_K);
+    StageDesc* dtab = static_cast<StageDesc*>(mem.alloc(tab.size() * sizeof(StageDesc), false));
+    CK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(StageDesc), cudaMemcpyHostToDevice));
     p.ktab = dtab; p.num_k = (int)tab.size();
+    p.b_taps = b_taps; p.a_half_off = d.a_half_off;
     p.tiles_w = d.tiles_w; p.tiles_h = d.tiles_h; p.tiles_b = d.tiles_b;
     p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
     p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
-    p.stages = pick_stages(d.block_n);
+    p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps);
     p.dbg = getenv("SR3_DBG") ? atoi(getenv("SR3_DBG")) : 0;
     p.n_tiles = d.n_tiles; p.nz = d.nz;
     p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
@@ -232,7 +252,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.tma_epi = (d.mode == 0 && getenv("SR3_NO_TMA_EPI") == nullptr && (d.out_f32 || d.resid)) ? 1 : 0;
     if (p.tma_epi) {
         const int w_sub = d.w_box < 32 ? d.w_box : 32, h_sub = 32 / w_sub;
-        REQUIRE(d.w_box % w_sub == 0 && (d.h_box % h_sub == 0 || d.h_box == 1), "tile box %dx%d cannot be split into per-warp boxes", d.w_box, d.h_box);
+        REQUIRE(d.w_box % w_sub == 0 && (d.h_box % h_sub == 0 || d.h_box == 1) && (h_sub == 1 || (128 / w_sub) % h_sub == 0), "tile box %dx%d cannot be split into per-warp boxes", d.w_box, d.h_box);
         auto mk = [&](const float* ptr, const OutSpec& o, bool& c4z) {
             c4z = (o.sB == 0 && o.sZ != 0);
             const long long s4 = c4z ? o.sZ : o.sB;
@@ -262,19 +282,46 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     if (const char* e = getenv("SR3_MAX_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }
     const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
-    const int kps = pick_kps(bn);
-    const int smem = gemm_smem_bytes(bn, kps, p.stages);
+    const int mh = d.mh;
+    const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
-    REQUIRE(bn == 16 || bn == 64 || bn == 128 || bn == 256, "unsupported block_n %d", bn);
-    return [p, grid, bn, kps, smem](cudaStream_t st) {
+    REQUIRE((bn == 16 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128)), "unsupported tile %dx%d", 128 * mh, bn);
+    return [p, grid, bn, mh, smem](cudaStream_t st) {
         switch (bn) {
-            case 16: launch_gemm_bn<16, 2>(p, grid, smem, st); break;
-            case 64: if (kps == 2) launch_gemm_bn<64, 2>(p, grid, smem, st); else launch_gemm_bn<64, 1>(p, grid, smem, st); break;
-            case 128: if (kps == 2) launch_gemm_bn<128, 2>(p, grid, smem, st); else launch_gemm_bn<128, 1>(p, grid, smem, st); break;
+            case 16: if (mh == 2) launch_gemm_bn<16, 2>(p, grid, smem, st); else launch_gemm_bn<16, 1>(p, grid, smem, st); break;
+            case 64: if (mh == 2) launch_gemm_bn<64, 2>(p, grid, smem, st); else launch_gemm_bn<64, 1>(p, grid, smem, st); break;
+            case 128: if (mh == 2) launch_gemm_bn<128, 2>(p, grid, smem, st); else launch_gemm_bn<128, 1>(p, grid, smem, st); break;
             default: launch_gemm_bn<256, 1>(p, grid, smem, st); break;
         }
     };
+}
+
+void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box);
+int pick_block_n(int cout);
+
+// Geometry of an image conv: the "tall halo" form for 3x3 stride-1 convs at >= 16x16, else a plain 128-pixel patch per tap.
+void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout) {
+    bool tall_ok = getenv("SR3_NO_TALL") == nullptr && OW >= 8 && OH >= 16, has3 = false;
+    for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh == -1) has3 = true; }
+    tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
+    if (tall_ok) {
+        d.tall = 1; d.mh = 2; d.w_box = 8;
+        if (OH >= 32) { d.h_box = 32; d.b_box = 1; d.a_box_w = 8; d.a_box_h = 34; d.a_box_b = 1; d.a_half_off = 16 * 1024; }
+        else { d.h_box = 16; d.b_box = 2; d.a_box_w = 8; d.a_box_h = 18; d.a_box_b = 2; d.a_half_off = 18 * 1024; }
+        int bn = cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 16);
+        if (bn == 128) {      // keep every SM busy: fall back to 64-wide tiles when 128-wide ones would leave SMs idle
+            const long long tiles128 = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box) * (cout / 128);
+            if (tiles128 < 100) bn = 64;
+        }
+        if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && cout % v == 0) bn = v; }
+        d.block_n = bn;
+    } else {
+        d.tall = 0; d.mh = 1;
+        pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
+        d.block_n = pick_block_n(cout);
+    }
+    d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = Bp / d.b_box;
 }
 
 void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box) {
@@ -420,7 +467,8 @@ struct sr3_engine {
     }
     bf16* new_weight(int rows, int ktot, int block_n) {
         if (dry) return nullptr;
-        const int rows_pad = ((rows + block_n - 1) / block_n) * block_n;
+        (void)block_n;
+        const int rows_pad = ((rows + 127) / 128) * 128;
         return static_cast<bf16*>(mem.alloc((size_t)rows_pad * ktot * sizeof(bf16)));
     }
     void push(Op op, int kind = 4, double flops = 0, double bytes = 0) {
@@ -484,11 +532,9 @@ struct sr3_engine {
         GemmDesc d;
         d.n_a = c.n_a; d.a[0] = c.a[0]; d.a[1] = c.a[1];
         d.slabs = c.slabs;
-        d.block_n = pick_block_n(c.cout);
-        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + d.block_n - 1) / d.block_n) * d.block_n;
-        pick_image_box(c.OW, c.OH, d.w_box, d.h_box, d.b_box);
-        d.tiles_w = c.OW / d.w_box; d.tiles_h = c.OH / d.h_box; d.tiles_b = Bp / d.b_box;
-        d.n_tiles = (int)(d.b_rows / d.block_n); d.nz = 1;
+        conv_geometry(d, c.OW, c.OH, Bp, c.cout);
+        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + 127) / 128) * 128;      // weights are padded to 128 rows (new_weight)
+        d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = 1;
         d.OW = c.OW; d.OH = c.OH; d.OB = B; d.n_valid = c.cout;
         d.bias = c.bias; d.bias2 = c.bias2; d.bias2_stride = c.bias2_stride;
         d.resid = c.resid; d.rs = nhwc_out(c.OH, c.OW, c.cout);
@@ -763,9 +809,8 @@ struct sr3_engine {
             if (!dry) {
                 GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C);
                 add_conv_slabs(d.slabs, 0, C, 3, 1, 0);
-                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 16;
-                pick_image_box(W, H, d.w_box, d.h_box, d.b_box);
-                d.tiles_w = W / d.w_box; d.tiles_h = H / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 1;
+                conv_geometry(d, W, H, Bp, 16);
+                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 128; d.n_tiles = 1;
                 d.mode = 1; d.OW = W; d.OH = H; d.OB = B; d.n_valid = co; d.bias = b; d.ctl = ctl_dev;
                 d.post.tab = post_tab; d.post.T = T_cap; d.post.H = H; d.post.W = W; d.post.C = co;
                 d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
@@ -1128,10 +1173,11 @@ int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
     add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
-    d.block_n = pick_block_n(Cout); d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
-    pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
+    conv_geometry(d, OW, OH, B, Cout);
+    d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
     REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
-    d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = B / d.b_box; d.n_tiles = Cout / d.block_n;
+    REQUIRE(Cout >= d.block_n, "Cout smaller than the tile");
+    d.n_tiles = Cout / d.block_n;
     d.OW = OW; d.OH = OH; d.OB = B; d.n_valid = Cout; d.bias = bias;
     d.out_f32 = y; d.os = nhwc_out(OH, OW, Cout);
     d.resid = r; d.rs = nhwc_out(OH, OW, Cout);
@@ -1165,10 +1211,11 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
     add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
-    d.block_n = pick_block_n(Cout); d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
-    pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
+    conv_geometry(d, OW, OH, B, Cout);
+    d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
     REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
-    d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = B / d.b_box; d.n_tiles = Cout / d.block_n;
+    REQUIRE(Cout >= d.block_n, "Cout smaller than the tile");
+    d.n_tiles = Cout / d.block_n;
     d.OW = OW; d.OH = OH; d.OB = B; d.n_valid = Cout; d.bias = bias;
     d.out_f32 = y; d.os = nhwc_out(OH, OW, Cout);
     d.stats = stats; d.stats_C = Cout;

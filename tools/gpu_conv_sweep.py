@@ -7,7 +7,7 @@ torch.zeros(1).cuda()
 SHAPES = {"hi64": (16, 128, 128, 64, 64), "hi128": (16, 128, 128, 128, 64), "mid128": (16, 64, 64, 128, 128), "mid256": (16, 32, 32, 256, 256),
           "lo512": (16, 8, 8, 512, 512), "lo16": (16, 16, 16, 512, 512)}
 def run(tag, shape, env=None, **kw):
-    for k in ("SR3_DBG", "SR3_STAGES", "SR3_MAX_CTAS", "SR3_NO_TMA_EPI", "SR3_BLOCK_N", "SR3_KPS64", "SR3_KPS128"):
+    for k in ("SR3_DBG", "SR3_STAGES", "SR3_MAX_CTAS", "SR3_NO_TMA_EPI", "SR3_BLOCK_N", "SR3_NO_TALL", "SR3_TALL_BN"):
         os.environ.pop(k, None)
     for k, v in (env or {}).items():
         os.environ[k] = str(v)
@@ -15,12 +15,12 @@ def run(tag, shape, env=None, **kw):
     ms = _native.bench_conv(B, H, W, ci, co, **kw)
     gf = 2.0 * B * H * W * ci * co * 9 / 1e9
     print(f"{shape:7s} {tag:34s} {ms*1000:8.1f} us  {gf/ms:8.1f} TF/s", flush=True)
-for shape in ("hi64", "hi128"):
-    run("kps64=2 default", shape)
-    run("kps64=1", shape, {"SR3_KPS64": 1})
-    run("kps64=2 no-work", shape, {"SR3_DBG": 57})
-for shape in ("mid128", "mid256", "lo16", "lo512"):
-    run("kps128=1 default", shape)
-    run("kps128=2", shape, {"SR3_KPS128": 2})
-    run("kps128=2 no-work", shape, {"SR3_DBG": 57, "SR3_KPS128": 2})
-    run("bn64", shape, {"SR3_BLOCK_N": 64})
+for shape in ("hi64", "hi128", "mid128", "mid256", "lo16", "lo512"):
+    run("tall default", shape)
+    run("tall resid", shape, resid=True)
+    run("generic (no tall)", shape, {"SR3_NO_TALL": 1})
+    run("tall bn64", shape, {"SR3_TALL_BN": 64})
+    run("tall bn128", shape, {"SR3_TALL_BN": 128})
+    run("tall dbg1 (no epi body)", shape, {"SR3_DBG": 1})
+    run("tall dbg57 (no work)", shape, {"SR3_DBG": 57})
+    run("tall dbg2 (no stats)", shape, {"SR3_DBG": 2})
