@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
     const int pix0 = blockIdx.x * p.pix_per_block;
     const int npix = min(p.pix_per_block, p.HW - pix0);
     const int total = npix * vec_per_pix;
-    constexpr int U = 4;          // independent 16-byte loads in flight per thread
+    constexpr int U = 8;          // independent 16-byte loads in flight per thread
     for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
         float4 x[U];
         long long pg[U];

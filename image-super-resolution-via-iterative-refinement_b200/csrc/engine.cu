@@ -65,7 +65,8 @@ CUtensorMap encode_map(int rank, const void* ptr, const uint64_t* dims, const ui
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i < rank - 1; ++i) gs[i] = strides_bytes[i];
-    for (int i = 0; i < rank; ++i) REQUIRE(box[i] >= 1 && box[i] <= 256 && box[i] <= dims[i], "TMA box %u exceeds dim %llu (axis %d)", box[i], (unsigned long long)dims[i], i);
+    // a box may be larger than the tensor extent (halo rows of small images): TMA zero-fills / clips the out-of-range part
+    for (int i = 0; i < rank; ++i) REQUIRE(box[i] >= 1 && box[i] <= 256, "TMA box %u out of range (axis %d)", box[i], i);
     REQUIRE((reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "TMA base not 16B aligned");
     for (int i = 0; i < rank - 1; ++i) REQUIRE(strides_bytes[i] % 16 == 0 && strides_bytes[i] > 0, "TMA stride %llu (axis %d) must be a positive multiple of 16", (unsigned long long)strides_bytes[i], i + 1);
     CUresult r = get_encode_fn()(&m, dtype, rank, const_cast<void*>(ptr), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -132,11 +133,11 @@ OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
 }
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
-int pick_stages(int block_n, int a_stage_bytes, int b_taps) {
+int pick_stages(int block_n, int a_stage_bytes, int b_taps, bool resid) {
     int s = GEMM_MAX_STAGES;
     if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    while (s > 1 && gemm_smem_bytes(block_n, a_stage_bytes, b_taps, s) > SMEM_LIMIT) --s;
+    while (s > 1 && gemm_smem_bytes(block_n, a_stage_bytes, b_taps, s, resid) > SMEM_LIMIT) --s;
     if (s < 1) s = 1;
     return s;
 }
@@ -240,7 +241,6 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.tiles_w = d.tiles_w; p.tiles_h = d.tiles_h; p.tiles_b = d.tiles_b;
     p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
     p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
-    p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps);
     p.dbg = getenv("SR3_DBG") ? atoi(getenv("SR3_DBG")) : 0;
     p.n_tiles = d.n_tiles; p.nz = d.nz;
     p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
@@ -283,7 +283,9 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
     const int mh = d.mh;
-    const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages);
+    const bool res_smem = p.tma_epi && d.resid != nullptr;
+    p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, res_smem);
+    const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
     REQUIRE((bn == 16 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128)), "unsupported tile %dx%d", 128 * mh, bn);
@@ -502,7 +504,7 @@ struct sr3_engine {
         const int C = p.C0 + p.C1;
         REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
         int ppb = 32768 / C;                                   // ~32 float4 per thread amortise the per-block statistics prologue
-        { const int cap = (int)(((long long)p.HW * B) / 296); if (ppb > cap) ppb = cap; }   // but keep >= 2 blocks per SM when possible
+        { const int cap = (int)(((long long)p.HW * B) / 1184); if (ppb > cap) ppb = cap; }  // but keep >= 8 blocks per SM when possible
         if (ppb < 1) ppb = 1; if (ppb > p.HW) ppb = p.HW;
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);

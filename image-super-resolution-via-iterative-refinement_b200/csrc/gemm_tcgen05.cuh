@@ -108,14 +108,14 @@ struct GemmParams {
 
 constexpr int GEMM_THREADS = 192;
 constexpr int GEMM_MAX_STAGES = 8;
-constexpr int GEMM_EPI_WARP_BYTES = 8192;    // per epilogue warp: 4 KB output staging + 4 KB residual staging
-constexpr int GEMM_EPI_BYTES = 4 * GEMM_EPI_WARP_BYTES;
+// per epilogue warp: 2 x 4 KB output staging (fp32 chunks for the TMA store) [+ 2 x 4 KB residual staging when the layer has one]
+__host__ __device__ constexpr int gemm_epi_bytes(bool resid) { return 4 * (resid ? 16384 : 8192); }
 constexpr int GEMM_MAX_K = 160;              // stages per tile (3x3 conv over 1024 ch tap by tap + 1x1 residual conv over 1024 ch)
 constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 48 /*stage table*/ + 4 * 2 * 32 * 4 /*per-warp bias staging*/;
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n, int a_stage_bytes, int b_taps) { return a_stage_bytes + b_taps * block_n * 128; }
-__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int a_stage_bytes, int b_taps, int stages) {
-    return stages * gemm_stage_bytes(block_n, a_stage_bytes, b_taps) + GEMM_EPI_BYTES + 1024 /*align slack*/ + GEMM_AUX_BYTES;
+__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int a_stage_bytes, int b_taps, int stages, bool resid) {
+    return stages * gemm_stage_bytes(block_n, a_stage_bytes, b_taps) + gemm_epi_bytes(resid) + 1024 /*align slack*/ + GEMM_AUX_BYTES;
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
@@ -215,16 +215,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     uint8_t* base_ptr = smem_raw + (base - raw);
     const int stages = p.stages;
     const int stage_bytes = p.a_stage_bytes + p.b_taps * B_BYTES;            // multiple of 1024
+    const bool use_res_tma = p.tma_epi && p.resid != nullptr;
+    const int epi_warp_bytes = use_res_tma ? 16384 : 8192;
+    const int epi_bytes = 4 * epi_warp_bytes;
     const uint32_t epi_base = base + stages * stage_bytes;
-    const uint32_t bar_base = epi_base + GEMM_EPI_BYTES;
+    const uint32_t bar_base = epi_base + epi_bytes;
     // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[4 warps]; then the TMEM slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + a); };
-    auto res_bar = [&](int w) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + w); };
-    uint8_t* aux_ptr = base_ptr + stages * stage_bytes + GEMM_EPI_BYTES;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 8));
+    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };
+    uint8_t* aux_ptr = base_ptr + stages * stage_bytes + epi_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 12));
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
     StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
     float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + GEMM_MAX_K * 48);
@@ -251,7 +254,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 4);       // one arrive per epilogue warp
         }
-        for (int w = 0; w < 4; ++w) mbar_init(res_bar(w), 1);
+        for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -342,15 +345,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     } else {
         // ---------------------------------------------------- epilogue: 4 warps, one TMEM lane quadrant each
         const int q = warp & 3;
-        const uint32_t out_smem = epi_base + q * GEMM_EPI_WARP_BYTES;       // 4 KB
-        const uint32_t res_smem = out_smem + 4096;                          // 4 KB
-        uint8_t* out_ptr = base_ptr + stages * stage_bytes + q * GEMM_EPI_WARP_BYTES;
-        uint8_t* res_ptr = out_ptr + 4096;
+        const uint32_t out_smem = epi_base + q * epi_warp_bytes;            // 2 x 4 KB
+        const uint32_t res_smem = out_smem + 8192;                          // 2 x 4 KB (layers with a residual only)
+        uint8_t* out_ptr = base_ptr + stages * stage_bytes + q * epi_warp_bytes;
+        uint8_t* res_ptr = out_ptr + 8192;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-        const bool use_res_tma = p.tma_epi && p.resid != nullptr;
         const bool use_out_tma = p.tma_epi && p.out_f32 != nullptr;
-        uint32_t res_phase = 0;
-        bool out_pending = false;
+        uint32_t res_phase = 0;        // bit b = parity of res_bar(q, b)
+        uint32_t res_count = 0;        // residual chunks consumed so far
+        uint32_t out_count = 0;        // output chunks staged so far (buffer = out_count & 1)
         // GroupNorm partial sums of this lane's column, kept in registers across tiles of the same (image, column block)
         constexpr int NCHS = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;
         float st_sum[NCHS], st_sq[NCHS];
@@ -397,8 +400,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     if (img0 != st_img || n0 != st_n0) { flush_stats(); st_img = img0; st_n0 = n0; }
                 }
                 if (use_res_tma && lane == 0) {            // residual chunk 0 of this row block: overlaps the main loop
-                    mbar_arrive_expect_tx(res_bar(q), 4096);
-                    tma_load_5d(res_smem, &p.res_map, res_bar(q), n0, w0 + sw, 0, h0 + sh, c4);
+                    const uint32_t b = res_count & 1;
+                    mbar_arrive_expect_tx(res_bar(q, b), 4096);
+                    tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0, w0 + sw, 0, h0 + sh, c4);
                 }
                 if (!waited) {
                     mbar_wait(tfull_bar(acc), (ti >> 1) & 1, 3);
@@ -444,6 +448,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         bs[lane] = bnext;
                         if (ch + 1 < NCH) bnext = load_bias(n0 + (ch + 1) * 32);
                         __syncwarp();
+                        if (use_res_tma) {
+                            ++res_count;                         // chunk ch is residual request number res_count
+                            if (ch + 1 < NCH && lane == 0) {     // request the next chunk into the other buffer (freed one chunk ago)
+                                const uint32_t b = res_count & 1;
+                                mbar_arrive_expect_tx(res_bar(q, b), 4096);
+                                tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0 + (ch + 1) * 32, w0 + sw, 0, h0 + sh, c4);
+                            }
+                        }
                         uint32_t v[32];
                         tmem_ld_32x32(t_acc + ch * 32, v);
                         tmem_ld_wait();
@@ -452,7 +464,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             __syncwarp();
                             if (lane == 0) mbar_arrive(tempty_bar(acc));
                         }
-                        if (p.dbg & 1) continue;
+                        if (p.dbg & 1) {
+                            if (use_res_tma) {
+                                const uint32_t b = (res_count - 1) & 1;
+                                mbar_wait(res_bar(q, b), (res_phase >> b) & 1u, 5);
+                                res_phase ^= (1u << b);
+                                __syncwarp();
+                            }
+                            continue;
+                        }
                         const int nb = n0 + ch * 32;
                         float f[32];
                         const bool full = (nb + 32 <= p.n_valid);
@@ -463,19 +483,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             f[j] = x;
                         }
                         if (use_res_tma) {
-                            mbar_wait(res_bar(q), res_phase, 5);
-                            res_phase ^= 1u;
-                            const uint8_t* rp = res_ptr + lane * 128;
+                            const uint32_t b = (res_count - 1) & 1;
+                            mbar_wait(res_bar(q, b), (res_phase >> b) & 1u, 5);
+                            res_phase ^= (1u << b);
+                            const uint8_t* rp = res_ptr + b * 4096 + lane * 128;
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
                                 const float4 r = *reinterpret_cast<const float4*>(rp + ((j ^ (lane & 7)) << 4));
                                 f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                             }
                             __syncwarp();                        // everyone is done with the buffer before it is re-requested
-                            if (ch + 1 < NCH && lane == 0) {
-                                mbar_arrive_expect_tx(res_bar(q), 4096);
-                                tma_load_5d(res_smem, &p.res_map, res_bar(q), n0 + (ch + 1) * 32, w0 + sw, 0, h0 + sh, c4);
-                            }
                         } else if (row_ok && p.resid) {
                             if (full) {
                                 const float4* r4 = reinterpret_cast<const float4*>(p.resid + ro + nb);
@@ -491,21 +508,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         }
                         if (p.dbg & 4) {
                         } else if (use_out_tma) {
-                            if (out_pending) {                   // the previous bulk store must have finished reading the staging buffer
-                                if (lane == 0) tma_store_wait_read<0>();
+                            const uint32_t ob = out_count & 1;
+                            if (out_count >= 2) {                // the bulk store issued two chunks ago must have finished reading its buffer
+                                if (lane == 0) tma_store_wait_read<1>();
                                 __syncwarp();
                             }
-                            uint8_t* op = out_ptr + lane * 128;
+                            uint8_t* op = out_ptr + ob * 4096 + lane * 128;
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
                                 *reinterpret_cast<float4*>(op + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
                             fence_proxy_async_smem();
                             __syncwarp();
                             if (lane == 0) {
-                                tma_store_5d(&p.out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
+                                tma_store_5d(&p.out_map, out_smem + ob * 4096, nb, w0 + sw, 0, h0 + sh, c4);
                                 tma_store_commit();
                             }
-                            out_pending = true;
+                            ++out_count;
                         } else if (row_ok && p.out_f32) {
                             if (full) {
                                 float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
@@ -548,11 +566,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             for (int c = 0; c < NCHS; ++c)
                                 if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
                         }
-                    }
-                    if ((p.dbg & 1) && use_res_tma) {            // keep the residual barrier phases consistent in timing experiments
-                        mbar_wait(res_bar(q), res_phase, 5);
-                        res_phase ^= 1u;
-                        __syncwarp();
                     }
                 }
             }
