@@ -6,7 +6,7 @@
 
 namespace sr3 {
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d) {
     __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
@@ -31,7 +31,9 @@ struct PrepParams {
     __nv_bfloat16* out_raw;                 // optional bf16(x), same shape
 };
 
-__global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
+// Block size = (C/4) * k threads: every thread owns ONE 4-channel column for the whole kernel (scale / shift live in
+// registers, no shared-memory or integer-division traffic in the streaming loop) and walks pixels k at a time.
+__global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
     extern __shared__ float sm[];
     const int C = p.C0 + p.C1;
     float* sc = sm;              // [C] scale   (first used as per-channel sum)
@@ -55,42 +57,40 @@ __global__ void __launch_bounds__(256) prep_kernel(const PrepParams p) {
         gm[g] = mean; gr[g] = rsqrtf(var + p.eps);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const int g = c / gs;
-        const float k = gr[g] * __ldg(&p.gamma[c]);
-        sc[c] = k; sh[c] = __ldg(&p.beta[c]) - gm[g] * k;
+    const int vpp = C >> 2;                       // 4-channel vectors per pixel
+    const int kpix = blockDim.x / vpp;            // pixels covered by the block per step
+    const int c = (threadIdx.x % vpp) << 2;       // this thread's channels (constant)
+    const int lp = threadIdx.x / vpp;             // this thread's pixel lane
+    float k4[4], s4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = (c + j) / gs;
+        const float k = gr[g] * __ldg(&p.gamma[c + j]);
+        k4[j] = k; s4[j] = __ldg(&p.beta[c + j]) - gm[g] * k;
     }
-    __syncthreads();
-    const int vec_per_pix = C >> 2;
+    const bool from0 = c < p.C0;
+    const float* src = from0 ? p.src0 + c : p.src1 + (c - p.C0);
+    const int cs = from0 ? p.C0 : p.C1;
     const int pix0 = blockIdx.x * p.pix_per_block;
-    const int npix = min(p.pix_per_block, p.HW - pix0);
-    const int total = npix * vec_per_pix;
-    constexpr int U = 8;          // independent 16-byte loads in flight per thread
-    for (int i0 = threadIdx.x; i0 < total; i0 += blockDim.x * U) {
+    const int pix1 = min(pix0 + p.pix_per_block, p.HW);
+    const long long img = static_cast<long long>(b) * p.HW;
+    constexpr int U = 4;                          // independent 16-byte loads in flight per thread
+    for (int pix = pix0 + lp; pix < pix1; pix += kpix * U) {
         float4 x[U];
-        long long pg[U];
-        int cc[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i < total) {
-                const int pix = pix0 + i / vec_per_pix;
-                cc[u] = (i % vec_per_pix) << 2;
-                pg[u] = static_cast<long long>(b) * p.HW + pix;
-                x[u] = (cc[u] < p.C0) ? __ldg(reinterpret_cast<const float4*>(p.src0 + pg[u] * p.C0 + cc[u]))
-                                      : __ldg(reinterpret_cast<const float4*>(p.src1 + pg[u] * p.C1 + (cc[u] - p.C0)));
-            }
+            const int pp = pix + u * kpix;
+            if (pp < pix1) x[u] = __ldg(reinterpret_cast<const float4*>(src + (img + pp) * cs));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int i = i0 + u * blockDim.x;
-            if (i < total) {
-                const int c = cc[u];
-                float y0 = x[u].x * sc[c] + sh[c], y1 = x[u].y * sc[c + 1] + sh[c + 1], y2 = x[u].z * sc[c + 2] + sh[c + 2],
-                      y3 = x[u].w * sc[c + 3] + sh[c + 3];
+            const int pp = pix + u * kpix;
+            if (pp < pix1) {
+                float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
                 if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                *reinterpret_cast<uint2*>(p.out_a + pg[u] * C + c) = pack_bf16x4(y0, y1, y2, y3);
-                if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + pg[u] * C + c) = pack_bf16x4(x[u].x, x[u].y, x[u].z, x[u].w);
+                const long long o = (img + pp) * C + c;
+                *reinterpret_cast<uint2*>(p.out_a + o) = pack_bf16x4(y0, y1, y2, y3);
+                if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = pack_bf16x4(x[u].x, x[u].y, x[u].z, x[u].w);
             }
         }
     }

@@ -160,6 +160,7 @@ void init_gemm_attrs() {
     if (done) return;
     CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    CK(cudaFuncSetAttribute(gemm_tile_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -288,10 +289,11 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
-    REQUIRE((bn == 16 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128)), "unsupported tile %dx%d", 128 * mh, bn);
+    REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128 && bn != 32)), "unsupported tile %dx%d", 128 * mh, bn);
     return [p, grid, bn, mh, smem](cudaStream_t st) {
         switch (bn) {
             case 16: if (mh == 2) launch_gemm_bn<16, 2>(p, grid, smem, st); else launch_gemm_bn<16, 1>(p, grid, smem, st); break;
+            case 32: launch_gemm_bn<32, 1>(p, grid, smem, st); break;
             case 64: if (mh == 2) launch_gemm_bn<64, 2>(p, grid, smem, st); else launch_gemm_bn<64, 1>(p, grid, smem, st); break;
             case 128: if (mh == 2) launch_gemm_bn<128, 2>(p, grid, smem, st); else launch_gemm_bn<128, 1>(p, grid, smem, st); break;
             default: launch_gemm_bn<256, 1>(p, grid, smem, st); break;
@@ -322,6 +324,9 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout) {
         d.tall = 0; d.mh = 1;
         pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
         d.block_n = pick_block_n(cout);
+        // few output pixels (8x8 levels): narrow tiles put every SM to work instead of 32 CTAs with a 72..144-slab K loop each
+        const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box);
+        if (getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 && mt * (cout / 128) < 64) d.block_n = (mt * (cout / 64) >= 100) ? 64 : 32;
     }
     d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = Bp / d.b_box;
 }
@@ -503,13 +508,18 @@ struct sr3_engine {
         p.out_a = out_a; p.out_raw = out_raw;
         const int C = p.C0 + p.C1;
         REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
-        int ppb = 32768 / C;                                   // ~32 float4 per thread amortise the per-block statistics prologue
-        { const int cap = (int)(((long long)p.HW * B) / 1184); if (ppb > cap) ppb = cap; }  // but keep >= 8 blocks per SM when possible
-        if (ppb < 1) ppb = 1; if (ppb > p.HW) ppb = p.HW;
+        const int vpp = C / 4;
+        REQUIRE(vpp <= 512, "GroupNorm over %d channels is not supported", C);
+        const int kpix = vpp >= 256 ? 1 : 256 / vpp;
+        const int threads = vpp * kpix;                                // <= 512, every thread owns one 4-channel column
+        int ppb = kpix * 4 * 8;                                        // 8 batches of 4 loads per thread
+        { const int cap = (int)(((long long)p.HW * B) / 1184); if (ppb > cap) ppb = cap; }   // keep ~8 blocks per SM when possible
+        if (ppb < kpix * 4) ppb = kpix * 4;
+        if (ppb > p.HW) ppb = p.HW;
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);
-        push([p, grid, smem](cudaStream_t st) { prep_kernel<<<grid, 256, smem, st>>>(p); CK(cudaGetLastError()); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
+        push([p, grid, smem, threads](cudaStream_t st) { prep_kernel<<<grid, threads, smem, st>>>(p); CK(cudaGetLastError()); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
     }
     void add_cast(const Act& s, bf16* dst, int up) {
         if (dry) return;

@@ -571,7 +571,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             }
         }
         if (p.stats && !(p.dbg & 2)) flush_stats();
-        if (use_out_tma && lane == 0) tma_store_wait_all<0>();      // smem must outlive the last bulk stores
+        if (use_out_tma && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
     }
     tc_fence_before();
     __syncthreads();
