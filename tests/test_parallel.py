@@ -1,0 +1,60 @@
+"""world_size-2 gloo tests (CPU) of the batch-sharding host logic used for multi-GPU sampling."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from sr3_b200 import parallel
+
+
+def test_shard_bounds_cover_and_balance():
+    for n in (0, 1, 2, 5, 16, 17):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        parallel.shard_bounds(4, 2, 2)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        cond = torch.rand(n, 3, 4, 4, generator=g)
+        x_T = torch.randn(n, 3, 4, 4, generator=g)
+
+        def fake_sampler(c, xt, first):          # deterministic function of (global index, inputs): stands in for the GPU loop
+            idx = torch.arange(first, first + xt.shape[0], dtype=torch.float32).view(-1, 1, 1, 1)
+            return c * 2 + xt + idx
+
+        out = parallel.sharded_sample(fake_sampler, cond, x_T)
+        ref = cond * 2 + x_T + torch.arange(n, dtype=torch.float32).view(-1, 1, 1, 1)
+        ret[rank] = bool(torch.equal(out, ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [16, 5])
+def test_sharded_sample_two_ranks_gloo(n):
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
