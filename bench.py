@@ -108,10 +108,42 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------------------
 # CPU legs (the only code here that touches oracle/)
 # ----------------------------------------------------------------------------------------------------------------------
+_CPU_THREADS = None
+
+
+def tune_cpu_threads():
+    """torch-CPU convs stop scaling (and can collapse) far below the core count of a 100+ core host: probe a few thread counts
+    on a tiny UNet forward and keep the fastest, as anyone running the reference on this box would."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    import torch
+    from oracle import sr3_oracle as orc
+    n = os.cpu_count() or 1
+    cands = sorted({c for c in (n, n // 2, 64, 32, 16, 8) if 1 <= c <= n}, reverse=True)
+    cfg = orc.UNetConfig(6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 0.2, 128)
+    sd = orc.init_state_dict(cfg, 0)
+    x = torch.randn(2, 6, 128, 128)
+    nl = torch.full((2, 1), 0.5)
+    best, best_t = cands[0], float("inf")
+    with torch.no_grad():
+        for c in cands:
+            torch.set_num_threads(c)
+            orc.unet_forward(sd, cfg, x, nl)
+            t0 = time.perf_counter()
+            orc.unet_forward(sd, cfg, x, nl)
+            dt = time.perf_counter() - t0
+            if dt < best_t:
+                best, best_t = c, dt
+    _CPU_THREADS = best
+    torch.set_num_threads(best)
+    return best
+
+
 def cpu_p_sample_time(batch, reps, warm=1):
     import torch
     from oracle import sr3_oracle as orc
-    torch.set_num_threads(os.cpu_count())
+    tune_cpu_threads()
     cfg = orc.UNetConfig(6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 0.2, 128)
     sd = orc.init_state_dict(cfg, 0)
     sch = orc.make_schedule(SCHED)
