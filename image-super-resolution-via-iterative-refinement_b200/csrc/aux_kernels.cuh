@@ -34,6 +34,8 @@ struct PrepParams {
 // Block size = (C/4) * k threads: every thread owns ONE 4-channel column for the whole kernel (scale / shift live in
 // registers, no shared-memory or integer-division traffic in the streaming loop) and walks pixels k at a time.
 __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     const int C = p.C0 + p.C1;
     float* sc = sm;              // [C] scale   (first used as per-channel sum)
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
 // fp32 NHWC -> bf16 NHWC, optionally nearest-2x upsampled (nn.Upsample(scale_factor=2,'nearest'), unet.py:58-65)
 __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int B, int H, int W,
                                                    int C, int up) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int OH = H * up, OW = W * up;
     const long long total = static_cast<long long>(B) * OH * OW * (C >> 2);
     const int vpp = C >> 2;
@@ -120,6 +124,8 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
 // one 128-row attention batch); keys outside get probability 0.
 __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows, int L,
                                                       int seg) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
@@ -144,6 +150,8 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
 
 // Start of a step: clear the GroupNorm statistics arena and advance the device-side timestep.
 __global__ void __launch_bounds__(256) step_begin_kernel(float4* stats, long long n4, StepCtl* ctl) {
+    pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<long long>(gridDim.x) * blockDim.x)
         stats[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -164,11 +172,14 @@ struct EmbedParams {
     int inner;
 };
 __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];
     const int inner = p.inner, hid = 4 * inner;
     float* pe = sm;            // [inner]
     float* h = sm + inner;     // [hid]
     const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
     const float nl = p.ctl->nl_from_table ? p.nl_table[p.ctl->t_cur + 1] : p.nl_buf[b];
     const int count = inner / 2;
     for (int j = threadIdx.x; j < inner; j += blockDim.x) {
@@ -178,31 +189,51 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
         pe[j] = j < count ? sinf(e) : cosf(e);
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < hid; j += blockDim.x) {
-        float a = p.b1[j];
-        for (int i = 0; i < inner; ++i) a += p.w1[j * inner + i] * pe[i];
-        h[j] = a / (1.0f + expf(-a));
+    for (int j = warp; j < hid; j += nwarp) {          // one warp per output: coalesced weight rows + shuffle reduction
+        float a = 0.f;
+        for (int i = lane; i < inner; i += 32) a += __ldg(&p.w1[j * inner + i]) * pe[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) { a += p.b1[j]; h[j] = a / (1.0f + expf(-a)); }
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < inner; j += blockDim.x) {
-        float a = p.b2[j];
-        for (int i = 0; i < hid; ++i) a += p.w2[j * hid + i] * h[i];
-        p.tau[b * inner + j] = a;
+    for (int j = warp; j < inner; j += nwarp) {
+        float a = 0.f;
+        for (int i = lane; i < hid; i += 32) a += __ldg(&p.w2[j * hid + i]) * h[i];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) p.tau[b * inner + j] = a + p.b2[j];
     }
 }
 
 // All FeatureWiseAffine projections at once (unet.py:34-50, bias-only form) + the block1 conv bias folded in:
 // film[b][j] = Wf[j] . tau[b] + bf[j] + cbias[j],  j over the concatenated Cout of every ResnetBlock.
+// A block owns 64 outputs: their weight rows are staged (coalesced) in padded smem together with tau of every image.
 __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ wf, const float* __restrict__ bf, const float* __restrict__ cbias,
-                                                   const float* __restrict__ tau, float* __restrict__ film, int F, int inner) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    const int b = blockIdx.y;
+                                                   const float* __restrict__ tau, float* __restrict__ film, int F, int inner, int B) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float sm[];
+    float* ws = sm;                          // [64][inner + 1]
+    float* ts = sm + 64 * (inner + 1);       // [B][inner]
+    const int j0 = blockIdx.x * 64;
+    for (int i = threadIdx.x; i < 64 * inner; i += blockDim.x) {
+        const int r = i / inner, c = i % inner;
+        ws[r * (inner + 1) + c] = (j0 + r < F) ? __ldg(&wf[static_cast<long long>(j0 + r) * inner + c]) : 0.f;
+    }
+    for (int i = threadIdx.x; i < B * inner; i += blockDim.x) ts[i] = __ldg(&tau[i]);
+    __syncthreads();
+    const int jl = threadIdx.x & 63, bq = threadIdx.x >> 6;
+    const int j = j0 + jl;
     if (j >= F) return;
-    float a = bf[j] + cbias[j];
-    const float* w = wf + static_cast<long long>(j) * inner;
-    const float* t = tau + b * inner;
-    for (int i = 0; i < inner; ++i) a += w[i] * t[i];
-    film[static_cast<long long>(b) * F + j] = a;
+    const float base = bf[j] + cbias[j];
+    const float* w = ws + jl * (inner + 1);
+    for (int b = bq; b < B; b += 4) {
+        float a = base;
+        const float* t = ts + b * inner;
+        for (int i = 0; i < inner; ++i) a += w[i] * t[i];
+        film[static_cast<long long>(b) * F + j] = a;
+    }
 }
 
 // OIHW fp32 conv weight -> K-major bf16 GEMM operand: dst[o][k_off + (r*KW+s)*cin_pad + c]

@@ -150,10 +150,22 @@ int num_sms() {
     }
     return n;
 }
+// Every kernel of the step is launched with programmatic stream serialization (PDL): its prologue overlaps the tail of the
+// previous kernel; the kernels call griddepcontrol.wait before touching upstream data.
+bool use_pdl() { static int v = -1; if (v < 0) v = getenv("SR3_NO_PDL") ? 0 : 1; return v == 1; }
+template <typename... KArgs, typename... Args>
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
+    CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
 template <int BN, int MH>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
-    gemm_tile_kernel<BN, MH><<<grid, GEMM_THREADS, smem, st>>>(p);
-    CK(cudaGetLastError());
+    launch_k(gemm_tile_kernel<BN, MH>, grid, dim3(GEMM_THREADS), (size_t)smem, st, p);
 }
 void init_gemm_attrs() {
     static bool done = false;
@@ -519,14 +531,14 @@ struct sr3_engine {
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);
-        push([p, grid, smem, threads](cudaStream_t st) { prep_kernel<<<grid, threads, smem, st>>>(p); CK(cudaGetLastError()); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
+        push([p, grid, smem, threads](cudaStream_t st) { launch_k(prep_kernel, grid, dim3(threads), (size_t)smem, st, p); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
     }
     void add_cast(const Act& s, bf16* dst, int up) {
         if (dry) return;
         const long long total = 1LL * B * s.H * up * s.W * up * (s.C / 4);
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
         const float* src = s.p; const int Bn = B, Hh = s.H, Ww = s.W, C = s.C;
-        push([=](cudaStream_t st) { cast_kernel<<<blocks, 256, 0, st>>>(src, dst, Bn, Hh, Ww, C, up); CK(cudaGetLastError()); }, 2, 0, (double)Bn * Hh * Ww * C * (4.0 + 2.0 * up * up));
+        push([=](cudaStream_t st) { launch_k(cast_kernel, dim3(blocks), dim3(256), 0, st, src, dst, Bn, Hh, Ww, C, up); }, 2, 0, (double)Bn * Hh * Ww * C * (4.0 + 2.0 * up * up));
     }
 
     // generic image conv: A sources already bf16; out fp32 NHWC (+stats)
@@ -674,7 +686,7 @@ struct sr3_engine {
         {
             const long long rows = (long long)nz * Lt;
             const int blocks = (int)((rows + 7) / 8);
-            push([=](cudaStream_t st) { softmax_kernel<<<blocks, 256, 0, st>>>(S, P, rows, Lt, HW); CK(cudaGetLastError()); }, 3, 0, (double)rows * Lt * 6.0);
+            push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW); }, 3, 0, (double)rows * Lt * 6.0);
         }
         {   // O[z] = P v : rows = queries, N = head dim, K = keys
             GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
@@ -747,13 +759,13 @@ struct sr3_engine {
             float4* sa = reinterpret_cast<float4*>(stats_arena);
             const long long n4 = (long long)(stats_cap / 4);
             StepCtl* c = ctl_dev;
-            push([=](cudaStream_t st) { step_begin_kernel<<<(int)std::min<long long>((n4 + 255) / 256, 592), 256, 0, st>>>(sa, n4, c); CK(cudaGetLastError()); });
+            push([=](cudaStream_t st) { launch_k(step_begin_kernel, dim3((int)std::min<long long>((n4 + 255) / 256, 592)), dim3(256), 0, st, sa, n4, c); });
             EmbedParams ep{}; ep.ctl = ctl_dev; ep.nl_table = nl_table; ep.nl_buf = nl_buf; ep.w1 = mlp_w1; ep.b1 = mlp_b1; ep.w2 = mlp_w2; ep.b2 = mlp_b2;
             ep.tau = tau; ep.inner = inner;
             const int Bn = B; const int esm = 5 * inner * 4;
-            push([=](cudaStream_t st) { embed_kernel<<<Bn, 256, esm, st>>>(ep); CK(cudaGetLastError()); });
+            push([=](cudaStream_t st) { launch_k(embed_kernel, dim3(Bn), dim3(256), (size_t)esm, st, ep); });
             float *fw = film_w, *fb = film_b, *fc = film_cb, *ta = tau, *fi = film; const int Fn = F, inn = inner;
-            push([=](cudaStream_t st) { film_kernel<<<dim3((Fn + 255) / 256, Bn), 256, 0, st>>>(fw, fb, fc, ta, fi, Fn, inn); CK(cudaGetLastError()); });
+            push([=](cudaStream_t st) { launch_k(film_kernel, dim3((Fn + 63) / 64), dim3(256), (size_t)((64 * (inn + 1) + Bn * inn) * 4), st, (const float*)fw, (const float*)fb, (const float*)fc, (const float*)ta, fi, Fn, inn, Bn); });
         }
 
         int film_off = 0;

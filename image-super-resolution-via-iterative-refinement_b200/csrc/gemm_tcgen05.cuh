@@ -265,6 +265,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();      // the next kernel may be scheduled onto SMs as our CTAs retire ...
+    pdl_wait();                   // ... and we touch upstream activations / statistics only after the previous kernel completed
 
     auto decode = [&](int tile, int& w0, int& h0, int& b0, int& n0, int& z) {
         const int tm = tile % tiles_m;          // m fastest: a CTA's consecutive tiles share the weight slab and mostly the image

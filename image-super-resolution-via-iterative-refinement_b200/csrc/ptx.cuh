@@ -24,6 +24,11 @@ __device__ __forceinline__ bool elect_one_sync() {
     return pred != 0;
 }
 
+// Programmatic dependent launch: the next kernel of the stream may start (and run its prologue) while this one drains;
+// nothing produced by an earlier kernel may be touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ uint64_t globaltimer_ns() {
     uint64_t t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
