@@ -209,6 +209,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SR3_NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line only)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     assert GLOBAL_BATCH % world == 0

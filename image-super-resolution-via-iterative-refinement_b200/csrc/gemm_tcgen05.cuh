@@ -106,12 +106,14 @@ struct GemmParams {
     PostParams post;
 };
 
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two groups of four)
+constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_MAX_STAGES = 8;
-// per epilogue warp: 2 x 4 KB output staging (fp32 chunks for the TMA store) [+ 2 x 4 KB residual staging when the layer has one]
-__host__ __device__ constexpr int gemm_epi_bytes(bool resid) { return 4 * (resid ? 16384 : 8192); }
+// per epilogue warp: 4 KB output staging (fp32 chunk for the TMA store) [+ 2 x 4 KB residual staging when the layer has one]
+__host__ __device__ constexpr int gemm_epi_warp_bytes(bool resid) { return resid ? 12288 : 4096; }
+__host__ __device__ constexpr int gemm_epi_bytes(bool resid) { return GEMM_EPI_WARPS * gemm_epi_warp_bytes(resid); }
 constexpr int GEMM_MAX_K = 160;              // stages per tile (3x3 conv over 1024 ch tap by tap + 1x1 residual conv over 1024 ch)
-constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 48 /*stage table*/ + 4 * 2 * 32 * 4 /*per-warp bias staging*/;
+constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 48 /*stage table*/ + GEMM_EPI_WARPS * 2 * 32 * 4 /*per-warp bias staging*/;
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n, int a_stage_bytes, int b_taps) { return a_stage_bytes + b_taps * block_n * 128; }
 __host__ __device__ constexpr int gemm_smem_bytes(int block_n, int a_stage_bytes, int b_taps, int stages, bool resid) {
@@ -216,8 +218,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     const int stages = p.stages;
     const int stage_bytes = p.a_stage_bytes + p.b_taps * B_BYTES;            // multiple of 1024
     const bool use_res_tma = p.tma_epi && p.resid != nullptr;
-    const int epi_warp_bytes = use_res_tma ? 16384 : 8192;
-    const int epi_bytes = 4 * epi_warp_bytes;
+    const int epi_warp_bytes = gemm_epi_warp_bytes(use_res_tma);
+    const int epi_bytes = GEMM_EPI_WARPS * epi_warp_bytes;
     const uint32_t epi_base = base + stages * stage_bytes;
     const uint32_t bar_base = epi_base + epi_bytes;
     // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[4 warps]; then the TMEM slot
@@ -225,9 +227,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + a); };
-    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };
+    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };   // w in [0, 8)
     uint8_t* aux_ptr = base_ptr + stages * stage_bytes + epi_bytes;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 12));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS));
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
     StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
     float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + GEMM_MAX_K * 48);
@@ -252,9 +254,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);       // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), GEMM_EPI_WARPS);   // one arrive per epilogue warp
         }
-        for (int w = 0; w < 4; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
+        for (int w = 0; w < GEMM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -345,17 +347,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             }
         }
     } else {
-        // ---------------------------------------------------- epilogue: 4 warps, one TMEM lane quadrant each
+        // ---------------------------------------------------- epilogue: 2 groups x 4 warps; a warp owns one TMEM lane quadrant and
+        // every second 32-column chunk of it, so eight warps hide each other's tcgen05.ld / shuffle / fence latencies
         const int q = warp & 3;
-        const uint32_t out_smem = epi_base + q * epi_warp_bytes;            // 2 x 4 KB
-        const uint32_t res_smem = out_smem + 8192;                          // 2 x 4 KB (layers with a residual only)
-        uint8_t* out_ptr = base_ptr + stages * stage_bytes + q * epi_warp_bytes;
-        uint8_t* res_ptr = out_ptr + 8192;
+        const int ew = warp - 2;                                            // 0..7
+        const int grp = ew >> 2;
+        const uint32_t out_smem = epi_base + ew * epi_warp_bytes;           // 4 KB
+        const uint32_t res_smem = out_smem + 4096;                          // 2 x 4 KB (layers with a residual only)
+        uint8_t* out_ptr = base_ptr + stages * stage_bytes + ew * epi_warp_bytes;
+        uint8_t* res_ptr = out_ptr + 4096;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const bool use_out_tma = p.tma_epi && p.out_f32 != nullptr;
         uint32_t res_phase = 0;        // bit b = parity of res_bar(q, b)
         uint32_t res_count = 0;        // residual chunks consumed so far
-        uint32_t out_count = 0;        // output chunks staged so far (buffer = out_count & 1)
+        bool out_pending = false;      // a bulk store from the staging buffer may still be reading it
         // GroupNorm partial sums of this lane's column, kept in registers across tiles of the same (image, column block)
         constexpr int NCHS = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;
         float st_sum[NCHS], st_sq[NCHS];
@@ -377,48 +382,61 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
 #pragma unroll
             for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
         };
+        constexpr int NCH = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;      // 32-column chunks per 128-row half
+        constexpr int NITEMS = MH * NCH;                            // work items (half, chunk) per tile; this warp takes item % 2 == grp
         int ti = 0;
         for (int tile = tile_begin; tile < tile_end; ++tile, ++ti) {
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int acc = ti & 1;
-            bool waited = false;
+            // geometry of a work item: rows of `half`, columns of `ch`
+            auto item_geom = [&](int item, int& half, int& ch, int& sw, int& sh, int& c4) {
+                half = item / NCH; ch = item % NCH;
+                const int r0 = half * 128 + q * 32;
+                sw = r0 % p.w_box;
+                sh = (r0 / p.w_box) % p.h_box;
+                const int sb = r0 / (p.w_box * p.h_box);
+                c4 = p.epi_c4_is_z ? z : (b0 + sb);
+            };
+            auto request_resid = [&](int item) {                   // lane 0 only
+                int half, ch, sw, sh, c4;
+                item_geom(item, half, ch, sw, sh, c4);
+                const uint32_t b = res_count & 1;
+                mbar_arrive_expect_tx(res_bar(ew, b), 4096);
+                tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(ew, b), n0 + ch * 32, w0 + sw, 0, h0 + sh, c4);
+            };
+            const bool has_work = grp < NITEMS;
+            if (use_res_tma && has_work && lane == 0) request_resid(grp);     // overlaps the main loop
+            mbar_wait(tfull_bar(acc), (ti >> 1) & 1, 3);
+            tc_fence_after();
+            if (!has_work) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+                continue;
+            }
 #pragma unroll 1
-            for (int half = 0; half < MH; ++half) {
+            for (int item = grp; item < NITEMS; item += 2) {
+                int half, ch, sw, sh, c4;
+                item_geom(item, half, ch, sw, sh, c4);
+                const bool last_item = (item + 2 >= NITEMS);
                 const int row = half * 128 + q * 32 + lane;
                 const int w = row % p.w_box;
                 const int h = (row / p.w_box) % p.h_box;
                 const int bb = row / (p.w_box * p.h_box);
-                // origin of this warp's 32-row sub-box inside the tile
-                const int r0 = half * 128 + q * 32;
-                const int sw = r0 % p.w_box;
-                const int sh = (r0 / p.w_box) % p.h_box;
-                const int sb = r0 / (p.w_box * p.h_box);
                 const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
                 const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
-                const int c4 = p.epi_c4_is_z ? z : (b0 + sb);
                 if (p.stats && !(p.dbg & 2)) {
                     const int img0 = __shfl_sync(0xffffffffu, img, 0);      // all rows of a warp belong to one image
                     if (img0 != st_img || n0 != st_n0) { flush_stats(); st_img = img0; st_n0 = n0; }
                 }
-                if (use_res_tma && lane == 0) {            // residual chunk 0 of this row block: overlaps the main loop
-                    const uint32_t b = res_count & 1;
-                    mbar_arrive_expect_tx(res_bar(q, b), 4096);
-                    tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0, w0 + sw, 0, h0 + sh, c4);
-                }
-                if (!waited) {
-                    mbar_wait(tfull_bar(acc), (ti >> 1) & 1, 3);
-                    tc_fence_after();
-                    waited = true;
-                }
                 const uint32_t t_acc = t_lane + acc * ACC_COLS + half * BLOCK_N;
-                const bool last_half = (half == MH - 1);
 
                 if constexpr (BLOCK_N == 16) {
                     uint32_t v[16];
                     tmem_ld_32x16(t_acc, v);
                     tmem_ld_wait();
-                    if (last_half) {
+                    if (last_item) {
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(tempty_bar(acc));
@@ -429,151 +447,127 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         final_epilogue(p, eps, img, oh, ow);
                     }
                 } else {
-                    const float* bias2 = p.bias2 ? p.bias2 + static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride : nullptr;
-                    const long long ro = (p.resid && !use_res_tma) ? out_index(p.rs, z, img, oh, ow) : 0;
-                    const long long oo = (p.out_f32 && !use_out_tma) ? out_index(p.os, z, img, oh, ow) : 0;
-                    const long long ho = p.out_bf16 ? out_index(p.hs, z, img, oh, ow) : 0;
-                    constexpr int NCH = BLOCK_N / 32;
-                    // bias (+ per-image FiLM bias) of this lane's column, fetched one chunk ahead, broadcast through smem
-                    auto load_bias = [&](int nbq) -> float {
-                        float v = 0.f;
-                        if (nbq + lane < p.n_valid) {
-                            if (p.bias) v += __ldg(&p.bias[nbq + lane]);
-                            if (bias2) v += __ldg(&bias2[nbq + lane]);
-                        }
-                        return v;
-                    };
-                    float bnext = load_bias(n0);
-#pragma unroll 1
-                    for (int ch = 0; ch < NCH; ++ch) {
-                        float* bs = bias_s + (q * 2 + (ch & 1)) * 32;
-                        bs[lane] = bnext;
-                        if (ch + 1 < NCH) bnext = load_bias(n0 + (ch + 1) * 32);
+                    const int nb = n0 + ch * 32;
+                    // bias (+ per-image FiLM bias) of this lane's column, broadcast through smem
+                    float bv = 0.f;
+                    if (nb + lane < p.n_valid) {
+                        if (p.bias) bv += __ldg(&p.bias[nb + lane]);
+                        if (p.bias2) bv += __ldg(&p.bias2[static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride + nb + lane]);
+                    }
+                    float* bs = bias_s + (ew * 2 + ((item >> 1) & 1)) * 32;
+                    bs[lane] = bv;
+                    __syncwarp();
+                    if (use_res_tma) {
+                        ++res_count;                             // this item is residual request number res_count
+                        if (!last_item && lane == 0) request_resid(item + 2);   // other buffer: freed one item ago
+                    }
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_acc + ch * 32, v);
+                    tmem_ld_wait();
+                    if (last_item) {                             // this warp's share of the accumulator is read: hand it back
+                        tc_fence_before();
                         __syncwarp();
-                        if (use_res_tma) {
-                            ++res_count;                         // chunk ch is residual request number res_count
-                            if (ch + 1 < NCH && lane == 0) {     // request the next chunk into the other buffer (freed one chunk ago)
-                                const uint32_t b = res_count & 1;
-                                mbar_arrive_expect_tx(res_bar(q, b), 4096);
-                                tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(q, b), n0 + (ch + 1) * 32, w0 + sw, 0, h0 + sh, c4);
-                            }
-                        }
-                        uint32_t v[32];
-                        tmem_ld_32x32(t_acc + ch * 32, v);
-                        tmem_ld_wait();
-                        if (last_half && ch == NCH - 1) {        // accumulator fully read: hand it back to the MMA warp
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(tempty_bar(acc));
-                        }
-                        if (p.dbg & 1) {
-                            if (use_res_tma) {
-                                const uint32_t b = (res_count - 1) & 1;
-                                mbar_wait(res_bar(q, b), (res_phase >> b) & 1u, 5);
-                                res_phase ^= (1u << b);
-                                __syncwarp();
-                            }
-                            continue;
-                        }
-                        const int nb = n0 + ch * 32;
-                        float f[32];
-                        const bool full = (nb + 32 <= p.n_valid);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            float x = __uint_as_float(v[j]) * p.scale + bs[j];
-                            if (!full && nb + j >= p.n_valid) x = 0.f;
-                            f[j] = x;
-                        }
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    if (p.dbg & 1) {
                         if (use_res_tma) {
                             const uint32_t b = (res_count - 1) & 1;
-                            mbar_wait(res_bar(q, b), (res_phase >> b) & 1u, 5);
+                            mbar_wait(res_bar(ew, b), (res_phase >> b) & 1u, 5);
                             res_phase ^= (1u << b);
-                            const uint8_t* rp = res_ptr + b * 4096 + lane * 128;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 r = *reinterpret_cast<const float4*>(rp + ((j ^ (lane & 7)) << 4));
-                                f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-                            }
-                            __syncwarp();                        // everyone is done with the buffer before it is re-requested
-                        } else if (row_ok && p.resid) {
-                            if (full) {
-                                const float4* r4 = reinterpret_cast<const float4*>(p.resid + ro + nb);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 r = __ldg(&r4[j]);
-                                    f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
-                                }
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
-                            }
-                        }
-                        if (p.dbg & 4) {
-                        } else if (use_out_tma) {
-                            const uint32_t ob = out_count & 1;
-                            if (out_count >= 2) {                // the bulk store issued two chunks ago must have finished reading its buffer
-                                if (lane == 0) tma_store_wait_read<1>();
-                                __syncwarp();
-                            }
-                            uint8_t* op = out_ptr + ob * 4096 + lane * 128;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4*>(op + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                            fence_proxy_async_smem();
                             __syncwarp();
-                            if (lane == 0) {
-                                tma_store_5d(&p.out_map, out_smem + ob * 4096, nb, w0 + sw, 0, h0 + sh, c4);
-                                tma_store_commit();
-                            }
-                            ++out_count;
-                        } else if (row_ok && p.out_f32) {
-                            if (full) {
-                                float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
-#pragma unroll
-                                for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
-                            }
                         }
-                        if (row_ok && p.out_bf16) {
-                            if (full) {
-                                uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
+                        continue;
+                    }
+                    float f[32];
+                    const bool full = (nb + 32 <= p.n_valid);
 #pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    __nv_bfloat162 h0v = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
-                                    __nv_bfloat162 h1v = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
-                                    __nv_bfloat162 h2v = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
-                                    __nv_bfloat162 h3v = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
-                                    uint4 u;
-                                    u.x = *reinterpret_cast<uint32_t*>(&h0v); u.y = *reinterpret_cast<uint32_t*>(&h1v);
-                                    u.z = *reinterpret_cast<uint32_t*>(&h2v); u.w = *reinterpret_cast<uint32_t*>(&h3v);
-                                    o4[j] = u;
-                                }
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
-                            }
+                    for (int j = 0; j < 32; ++j) {
+                        float x = __uint_as_float(v[j]) * p.scale + bs[j];
+                        if (!full && nb + j >= p.n_valid) x = 0.f;
+                        f[j] = x;
+                    }
+                    if (use_res_tma) {
+                        const uint32_t b = (res_count - 1) & 1;
+                        mbar_wait(res_bar(ew, b), (res_phase >> b) & 1u, 5);
+                        res_phase ^= (1u << b);
+                        const uint8_t* rp = res_ptr + b * 4096 + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 r = *reinterpret_cast<const float4*>(rp + ((j ^ (lane & 7)) << 4));
+                            f[4 * j] += r.x; f[4 * j + 1] += r.y; f[4 * j + 2] += r.z; f[4 * j + 3] += r.w;
                         }
-                        if (p.stats && !(p.dbg & 2)) {
-                            float s1[32], s2[32];
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) {
-                                const float x = row_ok ? f[j] : 0.f;
-                                s1[j] = x; s2[j] = x * x;
-                            }
-                            const float cs = warp_column_sums(s1);
-                            const float cq = warp_column_sums(s2);
-#pragma unroll
-                            for (int c = 0; c < NCHS; ++c)
-                                if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
+                        __syncwarp();                            // everyone is done with the buffer before it is re-requested
+                    } else if (row_ok && p.resid) {
+                        const long long ro = out_index(p.rs, z, img, oh, ow);
+                        for (int j = 0; j < 32; ++j)
+                            if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
+                    }
+                    if (p.dbg & 4) {
+                    } else if (use_out_tma) {
+                        if (out_pending) {                       // the previous bulk store must have finished reading the staging buffer
+                            if (lane == 0) tma_store_wait_read<0>();
+                            __syncwarp();
                         }
+                        uint8_t* op = out_ptr + lane * 128;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            *reinterpret_cast<float4*>(op + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            tma_store_5d(&p.out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
+                            tma_store_commit();
+                        }
+                        out_pending = true;
+                    } else if (row_ok && p.out_f32) {
+                        const long long oo = out_index(p.os, z, img, oh, ow);
+                        if (full) {
+                            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) o4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
+                        }
+                    }
+                    if (row_ok && p.out_bf16) {
+                        const long long ho = out_index(p.hs, z, img, oh, ow);
+                        if (full) {
+                            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                __nv_bfloat162 h0v = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+                                __nv_bfloat162 h1v = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+                                __nv_bfloat162 h2v = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+                                __nv_bfloat162 h3v = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+                                uint4 uu;
+                                uu.x = *reinterpret_cast<uint32_t*>(&h0v); uu.y = *reinterpret_cast<uint32_t*>(&h1v);
+                                uu.z = *reinterpret_cast<uint32_t*>(&h2v); uu.w = *reinterpret_cast<uint32_t*>(&h3v);
+                                o4[j] = uu;
+                            }
+                        } else {
+                            for (int j = 0; j < 32; ++j)
+                                if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
+                        }
+                    }
+                    if (p.stats && !(p.dbg & 2)) {
+                        float s2[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float x = row_ok ? f[j] : 0.f;
+                            f[j] = x; s2[j] = x * x;
+                        }
+                        const float cs = warp_column_sums(f);
+                        const float cq = warp_column_sums(s2);
+#pragma unroll
+                        for (int c = 0; c < NCHS; ++c)
+                            if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
                     }
                 }
             }
         }
         if (p.stats && !(p.dbg & 2)) flush_stats();
-        if (use_out_tma && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
+        if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
     }
     tc_fence_before();
     __syncthreads();

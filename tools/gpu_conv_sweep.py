@@ -7,7 +7,7 @@ torch.zeros(1).cuda()
 SHAPES = {"hi64": (16, 128, 128, 64, 64), "hi128": (16, 128, 128, 128, 64), "mid128": (16, 64, 64, 128, 128), "mid256": (16, 32, 32, 256, 256),
           "lo512": (16, 8, 8, 512, 512), "lo16": (16, 16, 16, 512, 512)}
 def run(tag, shape, env=None, **kw):
-    for k in ("SR3_DBG", "SR3_STAGES", "SR3_MAX_CTAS", "SR3_NO_TMA_EPI", "SR3_BLOCK_N", "SR3_NO_TALL", "SR3_TALL_BN"):
+    for k in ("SR3_DBG", "SR3_STAGES", "SR3_MAX_CTAS", "SR3_NO_TMA_EPI", "SR3_BLOCK_N", "SR3_NO_TALL", "SR3_TALL_BN", "SR3_NO_PDL"):
         os.environ.pop(k, None)
     for k, v in (env or {}).items():
         os.environ[k] = str(v)
@@ -16,11 +16,7 @@ def run(tag, shape, env=None, **kw):
     gf = 2.0 * B * H * W * ci * co * 9 / 1e9
     print(f"{shape:7s} {tag:34s} {ms*1000:8.1f} us  {gf/ms:8.1f} TF/s", flush=True)
 for shape in ("hi64", "hi128", "mid128", "mid256", "lo16", "lo512"):
-    run("tall default", shape)
-    run("tall resid", shape, resid=True)
-    run("generic (no tall)", shape, {"SR3_NO_TALL": 1})
-    run("tall bn64", shape, {"SR3_TALL_BN": 64})
-    run("tall bn128", shape, {"SR3_TALL_BN": 128})
-    run("tall dbg1 (no epi body)", shape, {"SR3_DBG": 1})
-    run("tall dbg57 (no work)", shape, {"SR3_DBG": 57})
-    run("tall dbg2 (no stats)", shape, {"SR3_DBG": 2})
+    run("graph: default", shape)
+    run("graph: no-work (dbg57)", shape, {"SR3_DBG": 57})
+    run("graph: no epi body (dbg1)", shape, {"SR3_DBG": 1})
+    run("graph: default NO_PDL", shape, {"SR3_NO_PDL": 1})
