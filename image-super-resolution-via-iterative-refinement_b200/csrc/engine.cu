@@ -133,11 +133,11 @@ OutSpec nhwc_out(int H, int W, int C, long long off = 0) {
 }
 
 constexpr int SMEM_LIMIT = 232448;   // 227 KB opt-in maximum per CTA on sm_100
-int pick_stages(int block_n, int a_stage_bytes, int b_taps, bool resid) {
+int pick_stages(int block_n, int a_stage_bytes, int b_taps, bool resid, int num_k) {
     int s = GEMM_MAX_STAGES;
     if (const char* e = getenv("SR3_STAGES")) s = atoi(e);
     if (s > GEMM_MAX_STAGES) s = GEMM_MAX_STAGES;
-    while (s > 1 && gemm_smem_bytes(block_n, a_stage_bytes, b_taps, s, resid) > SMEM_LIMIT) --s;
+    while (s > 1 && gemm_smem_bytes(block_n, a_stage_bytes, b_taps, s, resid, num_k) > SMEM_LIMIT) --s;
     if (s < 1) s = 1;
     return s;
 }
@@ -223,14 +223,17 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
         REQUIRE(d.b_rows >= d.block_n, "B rows %lld < block_n %d", d.b_rows, d.block_n);
         p.b_map = encode_map(2, d.b_ptr, dims, str, box);
     }
-    // stage table: in tall mode the three vertical taps (dh = -1, 0, +1) of one (source, channel chunk, dw) share a stage
+    // stage table.  Tall mode: the three vertical taps (dh = -1, 0, +1) of one (source, channel chunk, dw) share one halo box.
+    // Generic mode: up to three consecutive K slabs of the same source are grouped into a stage (one box each).
     std::vector<StageDesc> tab;
-    int b_taps = 1;
+    int b_taps = 1, a_boxes = 1;
+    const int group_max = getenv("SR3_GROUP") ? atoi(getenv("SR3_GROUP")) : 3;
     for (size_t i = 0; i < d.slabs.size(); ++i) {
         const KSlab& k = d.slabs[i];
         REQUIRE(k.a_sel < d.n_a, "slab refers to missing A source");
         StageDesc e; memset(&e, 0, sizeof(e));
-        e.a_sel = k.a_sel; e.a_chan = k.a_chan; e.dw = k.dw; e.dh = k.dh; e.p = k.p; e.ntaps = 1; e.b_col0 = k.b_col;
+        e.a_sel = k.a_sel; e.ntaps = 1;
+        e.tap[0].a_chan = k.a_chan; e.tap[0].dw = k.dw; e.tap[0].dh = k.dh; e.tap[0].p = k.p; e.tap[0].b_col = k.b_col;
         if (d.tall) {
             REQUIRE(k.p == 0 && k.dh >= -1 && k.dh <= 1, "tall mode needs stride-1 taps");
             auto sibling = [&](int dh) -> const KSlab* {
@@ -238,14 +241,34 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
                 return nullptr;
             };
             const KSlab *s0 = sibling(-1), *s1 = sibling(0), *s2 = sibling(1);
-            const bool grouped = s0 && s1 && s2 && (s2->b_col - s1->b_col == s1->b_col - s0->b_col);
+            const bool grouped = s0 && s1 && s2;
             if (grouped && k.dh != -1) continue;          // folded into the dh = -1 stage
-            e.dh = -1;                                    // the box always starts one row above the tile
-            if (grouped) { e.ntaps = 3; e.b_col_step = s1->b_col - s0->b_col; e.a_off0 = 0; e.a_off_step = 1024; b_taps = 3; }
-            else { e.a_off0 = (k.dh + 1) * 1024; }
+            e.tap[0].dh = -1;                             // the box always starts one row above the tile
+            if (grouped) {
+                e.ntaps = 3; b_taps = 3;
+                const KSlab* sib[3] = {s0, s1, s2};
+                for (int t = 0; t < 3; ++t) { e.tap[t] = e.tap[0]; e.tap[t].b_col = sib[t]->b_col; e.tap[t].a_off = t * 1024; }
+            } else {
+                e.tap[0].a_off = (k.dh + 1) * 1024;
+            }
+        } else {
+            e.a_multi = 1;
+            int n = 1;
+            while (n < group_max && i + n < d.slabs.size() && d.slabs[i + n].a_sel == k.a_sel) ++n;
+            e.ntaps = n;
+            for (int t = 0; t < n; ++t) {
+                const KSlab& o = d.slabs[i + t];
+                e.tap[t].a_chan = o.a_chan; e.tap[t].dw = o.dw; e.tap[t].dh = o.dh; e.tap[t].p = o.p; e.tap[t].b_col = o.b_col;
+                e.tap[t].a_off = t * p.a_stage_bytes;     // boxes back to back (p.a_stage_bytes still holds ONE box here)
+            }
+            if (n > b_taps) b_taps = n;
+            if (n > a_boxes) a_boxes = n;
+            i += n - 1;
         }
         tab.push_back(e);
     }
+    p.a_box_bytes = p.a_stage_bytes;
+    p.a_stage_bytes = p.a_box_bytes * a_boxes;
     REQUIRE((int)tab.size() <= GEMM_MAX_K, "gemm with %d stages per tile (max %d)", (int)tab.size(), GEMM_MAX_K);
     StageDesc* dtab = static_cast<StageDesc*>(mem.alloc(tab.size() * sizeof(StageDesc), false));
     CK(cudaMemcpy(dtab, tab.data(), tab.size() * sizeof(StageDesc), cudaMemcpyHostToDevice));
@@ -297,8 +320,8 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     const int bn = d.block_n;
     const int mh = d.mh;
     const bool res_smem = p.tma_epi && d.resid != nullptr;
-    p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, res_smem);
-    const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem);
+    p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, res_smem, p.num_k);
+    const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem, p.num_k);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
     REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128 && bn != 32)), "unsupported tile %dx%d", 128 * mh, bn);
@@ -317,7 +340,7 @@ void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box);
 int pick_block_n(int cout);
 
 // Geometry of an image conv: the "tall halo" form for 3x3 stride-1 convs at >= 16x16, else a plain 128-pixel patch per tap.
-void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout) {
+void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid = false) {
     bool tall_ok = getenv("SR3_NO_TALL") == nullptr && OW >= 8 && OH >= 16, has3 = false;
     for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh == -1) has3 = true; }
     tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
@@ -330,6 +353,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout) {
             const long long tiles128 = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box) * (cout / 128);
             if (tiles128 < 100) bn = 64;
         }
+        if (bn == 128 && has_resid) bn = 64;   // residual staging (8 warps x 8 KB) would leave room for a single 84 KB stage
         if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && cout % v == 0) bn = v; }
         d.block_n = bn;
     } else {
@@ -556,7 +580,7 @@ struct sr3_engine {
         GemmDesc d;
         d.n_a = c.n_a; d.a[0] = c.a[0]; d.a[1] = c.a[1];
         d.slabs = c.slabs;
-        conv_geometry(d, c.OW, c.OH, Bp, c.cout);
+        conv_geometry(d, c.OW, c.OH, Bp, c.cout, c.resid != nullptr);
         d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + 127) / 128) * 128;      // weights are padded to 128 rows (new_weight)
         d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = 1;
         d.OW = c.OW; d.OH = c.OH; d.OB = B; d.n_valid = c.cout;
@@ -1197,7 +1221,7 @@ int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
     add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
-    conv_geometry(d, OW, OH, B, Cout);
+    conv_geometry(d, OW, OH, B, Cout, with_resid != 0);
     d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
     REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
     REQUIRE(Cout >= d.block_n, "Cout smaller than the tile");
@@ -1246,7 +1270,7 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
     add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
-    conv_geometry(d, OW, OH, B, Cout);
+    conv_geometry(d, OW, OH, B, Cout, with_resid != 0);
     d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
     REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
     REQUIRE(Cout >= d.block_n, "Cout smaller than the tile");

@@ -57,15 +57,22 @@ struct PostParams {
     int in_C, in_coff;
 };
 
-// One pipeline stage of the K loop (host-built table, copied to shared memory by the kernel).
-struct StageDesc {
-    int a_sel;       // which A tensor map
+// One pipeline stage of the K loop (host-built table, copied to shared memory by the kernel): up to three K slabs
+// (64 channels each).  Tall-halo stages load ONE activation box that serves all taps (a_multi = 0); generic stages load one
+// box per slab (a_multi = 1) -- grouping slabs only amortises the mbarrier handshake.
+struct StageTap {
     int a_chan;      // channel coordinate (dim 0) of the A box
     int dw, dh, p;   // box shift along W', H' and the parity coordinate
-    int ntaps;       // weight tiles in this stage (1..3)
-    int b_col0, b_col_step;   // B column (K coordinate) of tap t = b_col0 + t * b_col_step
-    int a_off0, a_off_step;   // byte offset of tap t's first row inside the A stage buffer (multiples of 1024)
-    int pad0, pad1;
+    int b_col;       // B column (K coordinate)
+    int a_off;       // byte offset of this tap's first row inside the A stage buffer (multiple of 1024)
+};
+struct StageDesc {
+    int ntaps;       // K slabs in this stage (1..3)
+    int a_multi;     // 1: every tap has its own A box (loaded at a_off), 0: one box (tap 0's coordinates) shared by all taps
+    int a_sel;       // which A tensor map
+    int pad0;
+    StageTap tap[3];
+    int pad1, pad2;  // 96 bytes = 6 x int4
 };
 
 struct GemmParams {
@@ -75,7 +82,8 @@ struct GemmParams {
     CUtensorMap res_map;     // fp32 residual, same geometry
     const StageDesc* ktab;   // [num_k]
     int num_k;
-    int a_stage_bytes;       // bytes of the A box (multiple of 1024)
+    int a_stage_bytes;       // bytes reserved for activation boxes per stage (multiple of 1024)
+    int a_box_bytes;         // bytes of ONE activation box (what a single TMA load delivers)
     int a_half_off;          // byte offset between the two 128-row halves inside the A buffer (MH = 2)
     int b_taps;              // weight tiles reserved per stage (max ntaps)
     int tiles_w, tiles_h, tiles_b;
@@ -112,12 +120,14 @@ constexpr int GEMM_MAX_STAGES = 8;
 // per epilogue warp: 4 KB output staging (fp32 chunk for the TMA store) [+ 2 x 4 KB residual staging when the layer has one]
 __host__ __device__ constexpr int gemm_epi_warp_bytes(bool resid) { return resid ? 12288 : 4096; }
 __host__ __device__ constexpr int gemm_epi_bytes(bool resid) { return GEMM_EPI_WARPS * gemm_epi_warp_bytes(resid); }
-constexpr int GEMM_MAX_K = 160;              // stages per tile (3x3 conv over 1024 ch tap by tap + 1x1 residual conv over 1024 ch)
-constexpr int GEMM_AUX_BYTES = 512 /*barriers*/ + GEMM_MAX_K * 48 /*stage table*/ + GEMM_EPI_WARPS * 2 * 32 * 4 /*per-warp bias staging*/;
+constexpr int GEMM_MAX_K = 160;              // stages per tile (<= 3 K slabs each); the table is sized per launch
+__host__ __device__ constexpr int gemm_aux_bytes(int num_k) {
+    return 512 /*barriers*/ + ((num_k * 96 + 127) / 128) * 128 /*stage table*/ + GEMM_EPI_WARPS * 2 * 32 * 4 /*per-warp bias staging*/;
+}
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n, int a_stage_bytes, int b_taps) { return a_stage_bytes + b_taps * block_n * 128; }
-__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int a_stage_bytes, int b_taps, int stages, bool resid) {
-    return stages * gemm_stage_bytes(block_n, a_stage_bytes, b_taps) + gemm_epi_bytes(resid) + 1024 /*align slack*/ + GEMM_AUX_BYTES;
+__host__ __device__ constexpr int gemm_smem_bytes(int block_n, int a_stage_bytes, int b_taps, int stages, bool resid, int num_k) {
+    return stages * gemm_stage_bytes(block_n, a_stage_bytes, b_taps) + gemm_epi_bytes(resid) + 1024 /*align slack*/ + gemm_aux_bytes(num_k);
 }
 
 // ---------------------------------------------------------------- Philox4x32-10 + Box-Muller
@@ -232,7 +242,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS));
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
     StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
-    float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + GEMM_MAX_K * 48);
+    float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + ((p.num_k * 96 + 127) / 128) * 128);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -241,7 +251,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     {
         const int4* src = reinterpret_cast<const int4*>(p.ktab);
         int4* dst = reinterpret_cast<int4*>(ktab_s);
-        for (int i = threadIdx.x; i < p.num_k * 3; i += GEMM_THREADS) dst[i] = __ldg(&src[i]);
+        for (int i = threadIdx.x; i < p.num_k * 6; i += GEMM_THREADS) dst[i] = __ldg(&src[i]);
     }
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.a_map[0]);
@@ -295,13 +305,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             for (int k = 0; k < p.num_k; ++k) {
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
-                    const StageDesc e = ktab_s[k];
+                    const StageDesc& e = ktab_s[k];
                     const uint32_t a_dst = base + s * stage_bytes;
-                    mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : p.a_stage_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
-                    if (!(p.dbg & 8)) tma_load_5d(a_dst, &p.a_map[e.a_sel], full_bar(s), e.a_chan, w0 + e.dw, e.p, h0 + e.dh, b0);
+                    const int na = e.a_multi ? e.ntaps : 1;
+                    mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : na * p.a_box_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
+                    if (!(p.dbg & 8)) {
+                        for (int t = 0; t < na; ++t)
+                            tma_load_5d(a_dst + e.tap[t].a_off, &p.a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
+                                        h0 + e.tap[t].dh, b0);
+                    }
                     if (!(p.dbg & 16)) {
                         for (int t = 0; t < e.ntaps; ++t)
-                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &p.b_map, full_bar(s), e.b_col0 + t * e.b_col_step, brow);
+                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &p.b_map, full_bar(s), e.tap[t].b_col, brow);
                     }
                 }
                 __syncwarp();
@@ -324,14 +339,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const StageDesc e = ktab_s[k];
+                    const StageDesc& e = ktab_s[k];
                     if (!(p.dbg & 32)) {
-                        const uint32_t a_lo = desc_lo0 + ((s * stage_bytes + e.a_off0) >> 4);
+                        const uint32_t a_lo = desc_lo0 + ((s * stage_bytes) >> 4);
                         const uint32_t b_lo = desc_lo0 + ((s * stage_bytes + p.a_stage_bytes) >> 4);
 #pragma unroll
                         for (int half = 0; half < MH; ++half) {
                             for (int t = 0; t < e.ntaps; ++t) {
-                                const uint64_t adesc = desc_hi | (a_lo + ((half * p.a_half_off + t * e.a_off_step) >> 4));
+                                const uint64_t adesc = desc_hi | (a_lo + ((half * p.a_half_off + e.tap[t].a_off) >> 4));
                                 const uint64_t bdesc = desc_hi | (b_lo + ((t * B_BYTES) >> 4));
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
