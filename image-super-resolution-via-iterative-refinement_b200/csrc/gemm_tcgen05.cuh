@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : na * p.a_box_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
                     if (!(p.dbg & 8)) {
                         for (int t = 0; t < na; ++t)
-                            tma_load_5d(a_dst + e.tap[t].a_off, &p.a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
+                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &p.a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
                                         h0 + e.tap[t].dh, b0);
                     }
                     if (!(p.dbg & 16)) {
