@@ -1270,7 +1270,7 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
     add_conv_slabs(d.slabs, 0, Cin, ksize, stride, 0);
-    conv_geometry(d, OW, OH, B, Cout, with_resid != 0);
+    conv_geometry(d, OW, OH, B, Cout);
     d.b_ptr = wp; d.b_K = ktot; d.b_rows = Cout;
     REQUIRE(B % d.b_box == 0, "batch must be a multiple of %d at this resolution", d.b_box);
     REQUIRE(Cout >= d.block_n, "Cout smaller than the tile");
