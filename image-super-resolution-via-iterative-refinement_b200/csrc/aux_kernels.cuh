@@ -251,6 +251,31 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
     }
 }
 
+// Weights of the four phase convs of a folded (nearest-2x -> conv3x3): for output parity py the kernel rows that land on low-res
+// row offset a are R(0,0)={0}, R(0,1)={1,2}, R(1,0)={0,1}, R(1,1)={2} (same for columns); summed in fp32, rounded once to bf16.
+// dst[phase][o][(a*2+b)*Cin + c]
+__global__ void __launch_bounds__(256) fold_upsample_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d0,
+                                                                   __nv_bfloat16* __restrict__ d1, __nv_bfloat16* __restrict__ d2,
+                                                                   __nv_bfloat16* __restrict__ d3, int Cout, int Cin) {
+    const long long total = 4LL * Cout * Cin * 4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int c = static_cast<int>(r % Cin); r /= Cin;
+        const int ab = static_cast<int>(r % 4); r /= 4;
+        const int o = static_cast<int>(r % Cout);
+        const int ph = static_cast<int>(r / Cout);
+        const int py = ph >> 1, px = ph & 1, a = ab >> 1, b = ab & 1;
+        const int r0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+        const int s0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+        float acc = 0.f;
+        for (int rr = r0; rr <= r1; ++rr)
+            for (int ss = s0; ss <= s1; ++ss) acc += src[((static_cast<long long>(o) * Cin + c) * 3 + rr) * 3 + ss];
+        __nv_bfloat16* d = ph == 0 ? d0 : (ph == 1 ? d1 : (ph == 2 ? d2 : d3));
+        d[static_cast<long long>(o) * (4 * Cin) + ab * Cin + c] = __float2bfloat16_rn(acc);
+    }
+}
+
 __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] + (b ? b[i] : 0.f);
