@@ -115,6 +115,7 @@ struct GemmDesc {
     int tall = 0;                                 // 3x3 stride-1 "tall halo" mode: A box = 8 x (rows + 2) pixels, vertical taps share it
     int a_box_w = 0, a_box_h = 0, a_box_b = 0;    // TMA box of the A operand (0: same as the tile patch)
     int a_half_off = 0;
+    int ksplit_max = 1;                           // split-K allowed up to this factor (image convs with few output tiles)
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
     // epilogue
@@ -314,13 +315,36 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     } else {
         p.out_map = p.b_map; p.res_map = p.b_map;
     }
-    const int total_tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz;
+    // split-K: when the output has too few tiles to occupy the SMs, several CTAs share a tile and each streams a slice of K
+    p.ksplit = 1;
+    {
+        const int tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz;
+        int ks = d.ksplit_max;
+        if (const char* e = getenv("SR3_KSPLIT")) ks = atoi(e);
+        if (ks > 1 && d.mode == 0 && d.out_f32 && d.block_n >= 32 && d.n_valid % 32 == 0) {
+            int want = num_sms() / tiles;                  // CTAs per tile that still fit one wave
+            if (want > ks) want = ks;
+            if (want > p.num_k / 2) want = p.num_k / 2;    // at least two stages per slice
+            if (want > 1) {
+                p.ksplit = want;
+                size_t elems = 0;                          // workspace with the addressing of out_f32
+                {
+                    const OutSpec& o = d.os;
+                    elems = (size_t)(o.off + (long long)(d.nz - 1) * o.sZ + (long long)(d.tiles_b * d.b_box - 1) * o.sB + (long long)(d.OH - 1) * o.sH +
+                                     (long long)(d.OW - 1) * o.sW + d.n_valid);
+                }
+                p.ws = static_cast<float*>(mem.alloc(elems * sizeof(float)));
+                p.counters = static_cast<unsigned int*>(mem.alloc((size_t)tiles * sizeof(unsigned int)));
+            }
+        }
+    }
+    const int total_tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz * p.ksplit;
     int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
     if (const char* e = getenv("SR3_MAX_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }
     const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
     const int mh = d.mh;
-    const bool res_smem = p.tma_epi && d.resid != nullptr;
+    const bool res_smem = p.tma_epi && d.resid != nullptr && p.ksplit <= 1;
     p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, res_smem, p.num_k);
     const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem, p.num_k);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
@@ -361,10 +385,12 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
         d.tall = 0; d.mh = 1;
         pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
         d.block_n = pick_block_n(cout);
-        // few output pixels (8x8 levels): narrow tiles put every SM to work instead of 32 CTAs with a 72..144-slab K loop each
+        // few output pixels (8x8 levels): 32-wide tiles put every SM to work (SR3_NARROW=1), or -- default -- keep wide tiles and split K
         const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box);
-        if (getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 && mt * (cout / 128) < 64) d.block_n = (mt * (cout / 64) >= 100) ? 64 : 32;
+        if (getenv("SR3_NARROW") && getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 && mt * (cout / 128) < 64)
+            d.block_n = (mt * (cout / 64) >= 100) ? 64 : 32;
     }
+    d.ksplit_max = getenv("SR3_NO_KSPLIT") ? 1 : 8;
     d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = Bp / d.b_box;
 }
 

@@ -90,6 +90,9 @@ struct GemmParams {
     int n_tiles, nz;         // persistent schedule: tile = m_tile + tiles_m * (n_tile + n_tiles * z); CTA c owns a contiguous range
     int tma_epi;             // 1: fp32 output / residual go through smem + TMA (out_map / res_map)
     int epi_c4_is_z;         // 5th coordinate of out_map / res_map: gemm-batch z (1) or image index (0)
+    int ksplit;              // split-K factor: ksplit CTAs share one output tile, partial sums meet in `ws` (fp32, same addressing as out_f32)
+    float* ws;               // zero between launches (the finalising CTA clears what it reads)
+    unsigned int* counters;  // [tiles] arrival counters, self resetting
     int dbg;                 // SR3_DBG bit mask (timing experiments only): 1 skip epilogue body, 2 skip stats, 4 skip out store,
                              // 8 skip A loads, 16 skip B loads, 32 skip MMAs
     int w_box, h_box, b_box; // pixel patch of one tile: w_box * h_box * b_box == MH * 128
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     uint8_t* base_ptr = smem_raw + (base - raw);
     const int stages = p.stages;
     const int stage_bytes = p.a_stage_bytes + p.b_taps * B_BYTES;            // multiple of 1024
-    const bool use_res_tma = p.tma_epi && p.resid != nullptr;
+    const bool use_res_tma = p.tma_epi && p.resid != nullptr && p.ksplit <= 1;
     const int epi_warp_bytes = gemm_epi_warp_bytes(use_res_tma);
     const int epi_bytes = GEMM_EPI_WARPS * epi_warp_bytes;
     const uint32_t epi_base = base + stages * stage_bytes;
@@ -240,6 +243,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };   // w in [0, 8)
     uint8_t* aux_ptr = base_ptr + stages * stage_bytes + epi_bytes;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS));
+    volatile uint32_t* split_flag = tmem_slot + 1;
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
     StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
     float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + ((p.num_k * 96 + 127) / 128) * 128);
@@ -247,7 +251,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
-    const int total_tiles = tiles_m * p.n_tiles * p.nz;
+    const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+    const int total_tiles = tiles_m * p.n_tiles * p.nz * ksplit;      // split index fastest: the CTAs of one output tile run together
     {
         const int4* src = reinterpret_cast<const int4*>(p.ktab);
         int4* dst = reinterpret_cast<int4*>(ktab_s);
@@ -280,7 +285,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     pdl_launch_dependents();      // the next kernel may be scheduled onto SMs as our CTAs retire ...
     pdl_wait();                   // ... and we touch upstream activations / statistics only after the previous kernel completed
 
-    auto decode = [&](int tile, int& w0, int& h0, int& b0, int& n0, int& z) {
+    auto decode = [&](int tile_s, int& w0, int& h0, int& b0, int& n0, int& z) {
+        const int tile = tile_s / ksplit;
         const int tm = tile % tiles_m;          // m fastest: a CTA's consecutive tiles share the weight slab and mostly the image
         const int r = tile / tiles_m;
         const int nt = r % p.n_tiles;
@@ -302,7 +308,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int brow = n0 + z * p.b_zrows;
-            for (int k = 0; k < p.num_k; ++k) {
+            const int sp = tile % ksplit;
+            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
+            for (int k = k0; k < k1; ++k) {
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
                     const StageDesc& e = ktab_s[k];
@@ -335,7 +343,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            for (int k = 0; k < p.num_k; ++k) {
+            const int sp = tile % ksplit;
+            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
+            for (int k = k0; k < k1; ++k) {
                 mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
@@ -350,12 +360,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 const uint64_t bdesc = desc_hi | (b_lo + ((t * B_BYTES) >> 4));
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
-                                    umma_bf16_ss(d_tmem + half * BLOCK_N, adesc + 2 * kk, bdesc + 2 * kk, IDESC, (k | t | kk) != 0);
+                                    umma_bf16_ss(d_tmem + half * BLOCK_N, adesc + 2 * kk, bdesc + 2 * kk, IDESC, ((k - k0) | t | kk) != 0);
                             }
                         }
                     }
                     umma_commit(empty_bar(s));
-                    if (k == p.num_k - 1) umma_commit(tfull_bar(acc));
+                    if (k == k1 - 1) umma_commit(tfull_bar(acc));
                 }
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
@@ -428,8 +438,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
-                continue;
             }
+            // pass 0 reads the accumulator from TMEM.  With split-K it only adds the partial sums into `ws`; the CTA that arrives
+            // last at the tile's counter runs pass 1, which reads the complete sums back and does the real epilogue.
+            const int npass = ksplit > 1 ? 2 : 1;
+#pragma unroll 1
+            for (int pass = 0; pass < npass; ++pass) {
+            if (pass == 1) {
+                __threadfence();
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (ew == 0 && lane == 0) {
+                    __threadfence();
+                    const unsigned int old = atomicAdd(p.counters + tile / ksplit, 1u);
+                    const bool last = (old == static_cast<unsigned int>(ksplit - 1));
+                    if (last) p.counters[tile / ksplit] = 0u;
+                    __threadfence();
+                    *split_flag = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const bool is_last = (*split_flag != 0u);
+                asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone has read the flag before it can be rewritten
+                if (!is_last) break;
+                __threadfence();
+            }
+            const bool from_ws = (pass == 1);
+            const bool to_ws = (ksplit > 1 && pass == 0);
+            if (has_work)
 #pragma unroll 1
             for (int item = grp; item < NITEMS; item += 2) {
                 int half, ch, sw, sh, c4;
@@ -441,7 +475,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 const int bb = row / (p.w_box * p.h_box);
                 const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
                 const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
-                if (p.stats && !(p.dbg & 2)) {
+                if (p.stats && !(p.dbg & 2) && !to_ws) {
                     const int img0 = __shfl_sync(0xffffffffu, img, 0);      // all rows of a warp belong to one image
                     if (img0 != st_img || n0 != st_n0) { flush_stats(); st_img = img0; st_n0 = n0; }
                 }
@@ -477,13 +511,41 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         if (!last_item && lane == 0) request_resid(item + 2);   // other buffer: freed one item ago
                     }
                     uint32_t v[32];
-                    tmem_ld_32x32(t_acc + ch * 32, v);
-                    tmem_ld_wait();
-                    if (last_item) {                             // this warp's share of the accumulator is read: hand it back
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    const long long wso = (ksplit > 1) ? out_index(p.os, z, img, oh, ow) + nb : 0;
+                    if (!from_ws) {
+                        tmem_ld_32x32(t_acc + ch * 32, v);
+                        tmem_ld_wait();
+                        if (last_item) {                         // this warp's share of the accumulator is read: hand it back
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                        }
+                        if (to_ws) {                             // split-K: add the scaled partial sums into the shared fp32 tile
+                            if (row_ok && nb + 32 <= p.n_valid) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.ws + wso + 4 * j),
+                                                 "f"(__uint_as_float(v[4 * j]) * p.scale), "f"(__uint_as_float(v[4 * j + 1]) * p.scale),
+                                                 "f"(__uint_as_float(v[4 * j + 2]) * p.scale), "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
+                                                 : "memory");
+                            }
+                            continue;
+                        }
+                    } else {                                     // finaliser: read the complete sums back (L2) and clear them
+                        if (row_ok && nb + 32 <= p.n_valid) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 r = __ldcg(reinterpret_cast<const float4*>(p.ws + wso) + j);
+                                v[4 * j] = __float_as_uint(r.x); v[4 * j + 1] = __float_as_uint(r.y);
+                                v[4 * j + 2] = __float_as_uint(r.z); v[4 * j + 3] = __float_as_uint(r.w);
+                                __stcg(reinterpret_cast<float4*>(p.ws + wso) + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = 0u;
+                        }
                     }
+                    const float ep_scale = from_ws ? 1.0f : p.scale;
                     if (p.dbg & 1) {
                         if (use_res_tma) {
                             const uint32_t b = (res_count - 1) & 1;
@@ -497,7 +559,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     const bool full = (nb + 32 <= p.n_valid);
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]) * p.scale + bs[j];
+                        float x = __uint_as_float(v[j]) * ep_scale + bs[j];
                         if (!full && nb + j >= p.n_valid) x = 0.f;
                         f[j] = x;
                     }
@@ -579,8 +641,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
                     }
                 }
-            }
-        }
+            }       // items
+            }       // pass
+        }           // tiles
         if (p.stats && !(p.dbg & 2)) flush_stats();
         if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
     }
