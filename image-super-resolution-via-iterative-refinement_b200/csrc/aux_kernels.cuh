@@ -189,20 +189,39 @@ __global__ void __launch_bounds__(256) embed_kernel(const EmbedParams p) {
         pe[j] = j < count ? sinf(e) : cosf(e);
     }
     __syncthreads();
-    for (int j = warp; j < hid; j += nwarp) {          // one warp per output: coalesced weight rows + shuffle reduction
-        float a = 0.f;
-        for (int i = lane; i < inner; i += 32) a += __ldg(&p.w1[j * inner + i]) * pe[i];
+    // one warp per output row (coalesced weights + shuffle reduction); 8 rows are in flight per warp so the L2 latency of the
+    // weight loads is paid once per batch of rows, not once per row
+    constexpr int R = 8;
+    for (int j0 = warp * R; j0 < hid; j0 += nwarp * R) {
+        float a[R];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) { a += p.b1[j]; h[j] = a / (1.0f + expf(-a)); }
+        for (int r = 0; r < R; ++r) {
+            a[r] = 0.f;
+            if (j0 + r < hid)
+                for (int i = lane; i < inner; i += 32) a[r] += __ldg(&p.w1[(j0 + r) * inner + i]) * pe[i];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+            if (lane == 0 && j0 + r < hid) { const float t = a[r] + p.b1[j0 + r]; h[j0 + r] = t / (1.0f + expf(-t)); }
+        }
     }
     __syncthreads();
-    for (int j = warp; j < inner; j += nwarp) {
-        float a = 0.f;
-        for (int i = lane; i < hid; i += 32) a += __ldg(&p.w2[j * hid + i]) * h[i];
+    for (int j0 = warp * R; j0 < inner; j0 += nwarp * R) {
+        float a[R];
 #pragma unroll
-        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) p.tau[b * inner + j] = a + p.b2[j];
+        for (int r = 0; r < R; ++r) {
+            a[r] = 0.f;
+            if (j0 + r < inner)
+                for (int i = lane; i < hid; i += 32) a[r] += __ldg(&p.w2[(j0 + r) * hid + i]) * h[i];
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) a[r] += __shfl_xor_sync(0xffffffffu, a[r], o);
+            if (lane == 0 && j0 + r < inner) p.tau[b * inner + j0 + r] = a[r] + p.b2[j0 + r];
+        }
     }
 }
 
