@@ -173,3 +173,32 @@ def test_state_dict_roundtrip_and_reload():
     net2.load_state_dict(sd, strict=True)
     e3 = net2.denoise_fn(x, nl)
     assert rel(e3, e1) < BF16_TOL      # not bit-identical: atomic-order noise in the GN sums flips bf16 roundings (~5e-3)
+
+
+def test_tiny_unconditional_loop_matches_oracle():
+    """sample() path (diffusion.py:180-187, 202-206): unconditional UNet (in_channel=3), seeded loop with injected noise."""
+    sched = {"schedule": "linear", "n_timestep": 6, "linear_start": 1e-4, "linear_end": 2e-2}
+    unet = dict(TINY_UNET, in_channel=3)
+    net = build(unet, 32, 5, conditional=False, sched=sched)
+    cfg = orc.UNetConfig(3, 3, 64, 32, (1, 2), (16,), 1, 0.0, 32)
+    sd = {k[len("denoise_fn."):]: v.detach().cpu() for k, v in net.state_dict().items() if k.startswith("denoise_fn.")}
+    sch = orc.make_schedule(sched)
+    g = torch.Generator().manual_seed(9)
+    x_T = torch.randn(2, 3, 32, 32, generator=g)
+    noises = torch.randn(6, 2, 3, 32, 32, generator=g)
+    with torch.no_grad():
+        ref = orc.p_sample_loop(sd, cfg, sch, None, x_T, list(noises), conditional=False, continous=True)
+    out = net.p_sample_loop((2, 3, 32, 32), continous=True, x_T=x_T.cuda(), noises=noises.cuda())
+    assert out.shape == ref.shape == (2 * (1 + 6), 3, 32, 32)
+    assert torch.equal(out[:2].cpu(), x_T)
+    assert rel(out, ref) < 2 * BF16_TOL, rel(out, ref)
+
+
+def test_sharded_super_resolution_single_rank(golden):
+    """parallel.sharded_super_resolution with world size 1 == plain super_resolution with the same Philox seed."""
+    from sr3_b200 import parallel
+    g = golden["tiny_diffusion"]
+    net = build(TINY_UNET, 32, 0, sched=g["sched"])
+    a = parallel.sharded_super_resolution(net, g["cond"], x_T=g["x_T"], seed=11)
+    b = net.super_resolution(g["cond"].cuda(), continous=True, x_T=g["x_T"].cuda(), seed=11, first_index=0)[-2:]
+    assert a.shape == (2, 3, 32, 32) and rel(a, b) < BF16_TOL
