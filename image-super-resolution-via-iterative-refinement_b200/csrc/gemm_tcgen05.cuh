@@ -432,6 +432,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             };
             const bool has_work = grp < NITEMS;
             if (use_res_tma && has_work && lane == 0) request_resid(grp);     // overlaps the main loop
+            // bias (+ per-image FiLM bias) of this lane's column for every work item of this warp: fetched now (there is no L1, an
+            // L2 round trip per item would sit on the critical path), broadcast through smem when the item is processed
+            constexpr int MAXI = (NITEMS + 1) / 2;
+            float bvs[MAXI];
+            if constexpr (BLOCK_N != 16) {
+#pragma unroll
+                for (int ii = 0; ii < MAXI; ++ii) {
+                    const int item = grp + 2 * ii;
+                    float bv = 0.f;
+                    if (item < NITEMS) {
+                        const int half = item / NCH, ch = item % NCH;
+                        const int bb = (half * 128 + q * 32) / (p.w_box * p.h_box);
+                        const int img = b0 + bb;
+                        const int n = n0 + ch * 32 + lane;
+                        if (n < p.n_valid) {
+                            if (p.bias) bv += __ldg(&p.bias[n]);
+                            if (p.bias2) bv += __ldg(&p.bias2[static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride + n]);
+                        }
+                    }
+                    bvs[ii] = bv;
+                }
+            }
             mbar_wait(tfull_bar(acc), (ti >> 1) & 1, 3);
             tc_fence_after();
             if (!has_work) {
@@ -497,12 +519,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     }
                 } else {
                     const int nb = n0 + ch * 32;
-                    // bias (+ per-image FiLM bias) of this lane's column, broadcast through smem
                     float bv = 0.f;
-                    if (nb + lane < p.n_valid) {
-                        if (p.bias) bv += __ldg(&p.bias[nb + lane]);
-                        if (p.bias2) bv += __ldg(&p.bias2[static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride + nb + lane]);
-                    }
+#pragma unroll
+                    for (int ii = 0; ii < MAXI; ++ii)
+                        if (item == grp + 2 * ii) bv = bvs[ii];
                     float* bs = bias_s + (ew * 2 + ((item >> 1) & 1)) * 32;
                     bs[lane] = bv;
                     __syncwarp();
