@@ -115,6 +115,7 @@ struct GemmDesc {
     int tall = 0;                                 // 3x3 stride-1 "tall halo" mode: A box = 8 x (rows + 2) pixels, vertical taps share it
     int a_box_w = 0, a_box_h = 0, a_box_b = 0;    // TMA box of the A operand (0: same as the tile patch)
     int a_half_off = 0;
+    bool b_is_param = false;                      // B operand is a packed weight matrix (constant within a step): eligible for L2 prefetch
     int ksplit_max = 1;                           // split-K allowed up to this factor (image convs with few output tiles)
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
@@ -198,6 +199,8 @@ struct DevAllocs {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
+struct GemmHandle { std::shared_ptr<GemmParams> p; const void* w_ptr = nullptr; long long w_bytes = 0; bool w_is_param = false; };
+static thread_local std::vector<GemmHandle>* g_gemm_registry = nullptr;   // set by the engine while it builds its plan
 
 // Turns a GemmDesc into a launchable op (encodes the TMA maps, uploads the K-slab table).
 Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
@@ -350,7 +353,13 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
     init_gemm_attrs();
     REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128 && bn != 32)), "unsupported tile %dx%d", 128 * mh, bn);
-    return [p, grid, bn, mh, smem](cudaStream_t st) {
+    std::shared_ptr<GemmParams> sp = std::make_shared<GemmParams>(p);
+    if (g_gemm_registry) {
+        GemmHandle h; h.p = sp; h.w_ptr = d.b_ptr; h.w_bytes = 2LL * d.b_rows * d.b_K; h.w_is_param = d.b_is_param;
+        g_gemm_registry->push_back(h);
+    }
+    return [sp, grid, bn, mh, smem](cudaStream_t st) {
+        const GemmParams& p = *sp;
         switch (bn) {
             case 16: if (mh == 2) launch_gemm_bn<16, 2>(p, grid, smem, st); else launch_gemm_bn<16, 1>(p, grid, smem, st); break;
             case 32: launch_gemm_bn<32, 1>(p, grid, smem, st); break;
@@ -454,6 +463,7 @@ struct sr3_engine {
     std::vector<ParamEntry> params;
     std::map<std::string, int> pindex;
     std::vector<Op> ops, finalize_ops;
+    std::vector<GemmHandle> gemms;          // tile-kernel launches of the step, in order (for next-layer weight prefetch)
     struct OpInfo { int kind; double flops; double bytes; };   // kind: 0 gemm, 1 groupnorm-apply, 2 cast/upsample, 3 softmax, 4 other
     std::vector<OpInfo> op_info;
     std::map<std::string, Act> taps;
@@ -613,6 +623,7 @@ struct sr3_engine {
         d.slabs = c.slabs;
         conv_geometry(d, c.OW, c.OH, Bp, c.cout, c.resid != nullptr);
         d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + 127) / 128) * 128;      // weights are padded to 128 rows (new_weight)
+        d.b_is_param = true;
         d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = 1;
         d.OW = c.OW; d.OH = c.OH; d.OB = B; d.n_valid = c.cout;
         d.bias = c.bias; d.bias2 = c.bias2; d.bias2_stride = c.bias2_stride;
@@ -713,7 +724,7 @@ struct sr3_engine {
         {   // q,k = Wqk n : [Bp*HW tokens] x [2C]
             GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C);
             add_conv_slabs(d.slabs, 0, C, 1, 1, 0);
-            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = 2 * C;
+            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = 2 * C; d.b_is_param = true;
             pick_image_box(Ww, Hh, d.w_box, d.h_box, d.b_box);
             d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 2 * C / 128;
             d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = 2 * C;
@@ -933,7 +944,7 @@ struct sr3_engine {
                 GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C);
                 add_conv_slabs(d.slabs, 0, C, 3, 1, 0);
                 conv_geometry(d, W, H, Bp, 16);
-                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 128; d.n_tiles = 1;
+                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 128; d.n_tiles = 1; d.b_is_param = true;
                 d.mode = 1; d.OW = W; d.OH = H; d.OB = B; d.n_valid = co; d.bias = b; d.ctl = ctl_dev;
                 d.post.tab = post_tab; d.post.T = T_cap; d.post.H = H; d.post.W = W; d.post.C = co;
                 d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
@@ -977,7 +988,19 @@ struct sr3_engine {
         post_tab = static_cast<float*>(mem.alloc((size_t)5 * T_cap * 4));
         // pass 2: real plan
         dry = false; stats_used = 0;
+        g_gemm_registry = &gemms;
         build_plan();
+        g_gemm_registry = nullptr;
+        if (getenv("SR3_NO_PREFETCH") == nullptr) {
+            // every tile kernel pulls the weights of the next one into L2 (the last one those of the next step's first)
+            for (size_t i = 0; i < gemms.size(); ++i) {
+                const GemmHandle& nx = gemms[(i + 1) % gemms.size()];
+                // attention "weights" (B operands that are activations produced by an earlier kernel of this step) are skipped
+                bool is_param = false;
+                is_param = nx.w_is_param;
+                if (is_param) { gemms[i].p->pf_ptr = nx.w_ptr; gemms[i].p->pf_bytes = nx.w_bytes & ~15ll; }
+            }
+        }
         CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
         CK(cudaDeviceSynchronize());
     }

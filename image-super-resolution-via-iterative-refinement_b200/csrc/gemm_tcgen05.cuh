@@ -93,6 +93,8 @@ struct GemmParams {
     int ksplit;              // split-K factor: ksplit CTAs share one output tile, partial sums meet in `ws` (fp32, same addressing as out_f32)
     float* ws;               // zero between launches (the finalising CTA clears what it reads)
     unsigned int* counters;  // [tiles] arrival counters, self resetting
+    const void* pf_ptr;      // weights of the NEXT tile-kernel launch: pulled into L2 while this launch runs (they would otherwise be
+    long long pf_bytes;      // first-touch HBM reads on the critical path of every pipeline stage of that launch)
     int dbg;                 // SR3_DBG bit mask (timing experiments only): 1 skip epilogue body, 2 skip stats, 4 skip out store,
                              // 8 skip A loads, 16 skip B loads, 32 skip MMAs
     int w_box, h_box, b_box; // pixel patch of one tile: w_box * h_box * b_box == MH * 128
@@ -282,6 +284,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (warp == 2 && lane == 0 && p.pf_bytes > 0) {                   // L2 prefetch of this CTA's slice of the next layer's weights
+        long long chunk = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15ll;
+        const long long off = chunk * blockIdx.x;
+        if (off < p.pf_bytes) {
+            if (off + chunk > p.pf_bytes) chunk = (p.pf_bytes - off) & ~15ll;
+            const char* src = static_cast<const char*>(p.pf_ptr) + off;
+            for (long long done = 0; done < chunk; done += 65536) {
+                const unsigned int n = static_cast<unsigned int>(chunk - done < 65536 ? chunk - done : 65536);
+                if (n >= 16) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src + done), "r"(n) : "memory");
+            }
+        }
+    }
     pdl_launch_dependents();      // the next kernel may be scheduled onto SMs as our CTAs retire ...
     pdl_wait();                   // ... and we touch upstream activations / statistics only after the previous kernel completed
 
