@@ -117,7 +117,6 @@ struct GemmDesc {
     int a_half_off = 0;
     bool b_is_param = false;                      // B operand is a packed weight matrix (constant within a step): eligible for L2 prefetch
     int ksplit_max = 1;                           // split-K allowed up to this factor (image convs with few output tiles)
-    int csk_max = 1;                              // cluster split-K (partials meet in distributed smem) allowed up to this cluster size
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
     // epilogue
@@ -157,31 +156,18 @@ int num_sms() {
 // previous kernel; the kernels call griddepcontrol.wait before touching upstream data.
 bool use_pdl() { static int v = -1; if (v < 0) v = getenv("SR3_NO_PDL") ? 0 : 1; return v == 1; }
 template <typename... KArgs, typename... Args>
-void launch_kc(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int cluster, Args&&... args) {
+void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    int n = 0;
-    if (use_pdl()) {
-        attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[n].val.programmaticStreamSerializationAllowed = 1;
-        ++n;
-    }
-    if (cluster > 1) {
-        attr[n].id = cudaLaunchAttributeClusterDimension;
-        attr[n].val.clusterDim.x = cluster; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1;
-        ++n;
-    }
-    cfg.attrs = attr; cfg.numAttrs = n;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
-}
-template <typename... KArgs, typename... Args>
-void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-    launch_kc(kernel, grid, block, smem, st, 1, std::forward<Args>(args)...);
 }
 template <int BN, int MH>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
-    launch_kc(gemm_tile_kernel<BN, MH>, grid, dim3(GEMM_THREADS), (size_t)smem, st, p.csk > 1 ? p.csk : 1, p);
+    launch_k(gemm_tile_kernel<BN, MH>, grid, dim3(GEMM_THREADS), (size_t)smem, st, p);
 }
 void init_gemm_attrs() {
     static bool done = false;
@@ -355,29 +341,16 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
             }
         }
     }
-    // cluster split-K: few output tiles and a long K loop -> the CTAs of a cluster each stream a slice of K and exchange partial
-    // tiles through distributed shared memory; one tile per cluster per launch
-    p.csk = 1;
-    if (p.ksplit == 1 && d.csk_max > 1 && d.mode == 0 && d.out_f32 && d.block_n >= 32 && d.n_valid % 32 == 0) {
-        const int tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz;
-        for (int c = d.csk_max; c >= 2; c >>= 1)
-            if (tiles * c <= num_sms() && p.num_k / c >= 2) { p.csk = c; break; }
-        // the partial tile is parked in the pipeline buffers: it must fit the stages this launch will have
-        const int st = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, false, p.num_k);
-        if (p.csk > 1 && d.mh * 128 * d.block_n * 4 > st * (p.a_stage_bytes + p.b_taps * d.block_n * 128)) p.csk = 1;
-    }
     const int total_tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz * p.ksplit;
     int ctas = total_tiles < num_sms() ? total_tiles : num_sms();
-    if (p.csk > 1) ctas = total_tiles * p.csk;
     if (const char* e = getenv("SR3_MAX_CTAS")) { int v = atoi(e); if (v > 0 && v < ctas) ctas = v; }
     const dim3 grid(ctas, 1, 1);
     const int bn = d.block_n;
     const int mh = d.mh;
-    const bool res_smem = p.tma_epi && d.resid != nullptr && p.ksplit <= 1 && p.csk <= 1;
+    const bool res_smem = p.tma_epi && d.resid != nullptr && p.ksplit <= 1;
     p.stages = pick_stages(d.block_n, p.a_stage_bytes, p.b_taps, res_smem, p.num_k);
     const int smem = gemm_smem_bytes(bn, p.a_stage_bytes, p.b_taps, p.stages, res_smem, p.num_k);
     REQUIRE(smem <= SMEM_LIMIT, "gemm shared memory %d exceeds the limit", smem);
-    if (p.csk > 1) REQUIRE(d.mh * 128 * d.block_n * 4 <= p.stages * (p.a_stage_bytes + p.b_taps * d.block_n * 128), "partial tile does not fit the pipeline buffers");
     init_gemm_attrs();
     REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128 && bn != 32)), "unsupported tile %dx%d", 128 * mh, bn);
     std::shared_ptr<GemmParams> sp = std::make_shared<GemmParams>(p);
@@ -425,12 +398,10 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
         // tested but measured slower here: 3.91 vs 3.57 ms/step at B=16, 2.65 vs 2.30 at B=2; the fp32 red.add traffic and the serial
         // finalising CTA cost more than the shorter K loops save.)
         const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box);
-        if (getenv("SR3_NO_CSK") != nullptr && getenv("SR3_KSPLIT") == nullptr && getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 &&
-            mt * (cout / 128) < 64)
+        if (getenv("SR3_KSPLIT") == nullptr && getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 && mt * (cout / 128) < 64)
             d.block_n = (mt * (cout / 64) >= 100) ? 64 : 32;
     }
     d.ksplit_max = getenv("SR3_KSPLIT") ? 8 : 1;
-    d.csk_max = (getenv("SR3_NO_CSK") || getenv("SR3_KSPLIT")) ? 1 : 8;
     d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = Bp / d.b_box;
 }
 

@@ -91,8 +91,6 @@ struct GemmParams {
     int tma_epi;             // 1: fp32 output / residual go through smem + TMA (out_map / res_map)
     int epi_c4_is_z;         // 5th coordinate of out_map / res_map: gemm-batch z (1) or image index (0)
     int ksplit;              // split-K factor: ksplit CTAs share one output tile, partial sums meet in `ws` (fp32, same addressing as out_f32)
-    int csk;                 // cluster split-K: the csk CTAs of a cluster share one output tile, partial tiles meet through distributed
-                             // shared memory (each CTA finalises a subset of the 32-column work items)
     float* ws;               // zero between launches (the finalising CTA clears what it reads)
     unsigned int* counters;  // [tiles] arrival counters, self resetting
     const void* pf_ptr;      // weights of the NEXT tile-kernel launch: pulled into L2 while this launch runs (they would otherwise be
@@ -234,7 +232,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     uint8_t* base_ptr = smem_raw + (base - raw);
     const int stages = p.stages;
     const int stage_bytes = p.a_stage_bytes + p.b_taps * B_BYTES;            // multiple of 1024
-    const bool use_res_tma = p.tma_epi && p.resid != nullptr && p.ksplit <= 1 && p.csk <= 1;
+    const bool use_res_tma = p.tma_epi && p.resid != nullptr && p.ksplit <= 1;
     const int epi_warp_bytes = gemm_epi_warp_bytes(use_res_tma);
     const int epi_bytes = GEMM_EPI_WARPS * epi_warp_bytes;
     const uint32_t epi_base = base + stages * stage_bytes;
@@ -256,8 +254,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     const int lane = threadIdx.x & 31;
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
-    const int csk = p.csk > 1 ? p.csk : 1;                            // exclusive with ksplit
-    const uint32_t crank = csk > 1 ? cluster_ctarank() : 0u;
     const int total_tiles = tiles_m * p.n_tiles * p.nz * ksplit;      // split index fastest: the CTAs of one output tile run together
     {
         const int4* src = reinterpret_cast<const int4*>(p.ktab);
@@ -315,10 +311,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         w0 = tw * p.w_box; h0 = th * p.h_box; b0 = tb * p.b_box + z * p.a_zstep; n0 = nt * BLOCK_N;
     };
     // contiguous tile range of this CTA (balanced to +-1 tile)
-    const int sched_id = blockIdx.x / csk, sched_n = gridDim.x / csk;          // clusters (or CTAs) that share the tile list
-    const int tile_begin = static_cast<int>((static_cast<long long>(total_tiles) * sched_id) / sched_n);
-    const int tile_end = static_cast<int>((static_cast<long long>(total_tiles) * (sched_id + 1)) / sched_n);
-    const int nsp = ksplit * csk;                                              // K slices per output tile
+    const int tile_begin = static_cast<int>((static_cast<long long>(total_tiles) * blockIdx.x) / gridDim.x);
+    const int tile_end = static_cast<int>((static_cast<long long>(total_tiles) * (blockIdx.x + 1)) / gridDim.x);
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer warp (converged; one elected lane issues)
@@ -328,8 +322,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int brow = n0 + z * p.b_zrows;
-            const int sp = csk > 1 ? static_cast<int>(crank) : tile % ksplit;
-            const int k0 = (p.num_k * sp) / nsp, k1 = (p.num_k * (sp + 1)) / nsp;
+            const int sp = tile % ksplit;
+            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
@@ -350,7 +344,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            if (csk > 1) { cluster_sync_all(); cluster_sync_all(); }    // the stage buffers hold the partial tiles until all peers read them
         }
     } else if (warp == 1) {
         // ---------------------------------------------------- MMA issuer warp (converged; one elected lane issues)
@@ -364,8 +357,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-            const int sp = csk > 1 ? static_cast<int>(crank) : tile % ksplit;
-            const int k0 = (p.num_k * sp) / nsp, k1 = (p.num_k * (sp + 1)) / nsp;
+            const int sp = tile % ksplit;
+            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
                 mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
@@ -391,7 +384,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 __syncwarp();
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
-            if (csk > 1) { cluster_sync_all(); cluster_sync_all(); }
         }
     } else {
         // ---------------------------------------------------- epilogue: 2 groups x 4 warps; a warp owns one TMEM lane quadrant and
@@ -485,12 +477,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             }
             // pass 0 reads the accumulator from TMEM.  With split-K it only adds the partial sums into `ws`; the CTA that arrives
             // last at the tile's counter runs pass 1, which reads the complete sums back and does the real epilogue.
-            const int npass = (ksplit > 1 || csk > 1) ? 2 : 1;
+            const int npass = ksplit > 1 ? 2 : 1;
 #pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
-            if (pass == 1 && csk > 1) {
-                cluster_sync_all();                                  // every CTA of the cluster has written its partial tile
-            } else if (pass == 1) {
+            if (pass == 1) {
                 __threadfence();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ew == 0 && lane == 0) {
@@ -508,19 +498,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 __threadfence();
             }
             const bool from_ws = (pass == 1);
-            const bool to_ws = (npass == 2 && pass == 0);
-            const bool part_mode = csk > 1;
-            int seen = 0;                                            // cluster mode, pass 1: items this CTA finalises, dealt to the two warp groups
+            const bool to_ws = (ksplit > 1 && pass == 0);
+            if (has_work)
 #pragma unroll 1
-            for (int item = (part_mode && pass == 1) ? 0 : grp; item < NITEMS; item += (part_mode && pass == 1) ? 1 : 2) {
-                if (part_mode && pass == 1) {
-                    if (item % csk != static_cast<int>(crank)) continue;
-                    if (((seen++) & 1) != grp) continue;
-                }
+            for (int item = grp; item < NITEMS; item += 2) {
                 int half, ch, sw, sh, c4;
                 item_geom(item, half, ch, sw, sh, c4);
                 const bool last_item = (item + 2 >= NITEMS);
-                const uint32_t part_off = static_cast<uint32_t>(((half * NCH + ch) * 4 + q) * 4096 + lane * 128);
                 const int row = half * 128 + q * 32 + lane;
                 const int w = row % p.w_box;
                 const int h = (row / p.w_box) % p.h_box;
@@ -570,15 +554,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             __syncwarp();
                             if (lane == 0) mbar_arrive(tempty_bar(acc));
                         }
-                        if (to_ws && part_mode) {                // cluster split-K: park the scaled partial tile in (idle) pipeline smem
-                            uint8_t* pp = base_ptr + part_off;
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4*>(pp + ((j ^ (lane & 7)) << 4)) =
-                                    make_float4(__uint_as_float(v[4 * j]) * p.scale, __uint_as_float(v[4 * j + 1]) * p.scale,
-                                                __uint_as_float(v[4 * j + 2]) * p.scale, __uint_as_float(v[4 * j + 3]) * p.scale);
-                            continue;
-                        }
                         if (to_ws) {                             // split-K: add the scaled partial sums into the shared fp32 tile
                             if (row_ok && nb + 32 <= p.n_valid) {
 #pragma unroll
@@ -590,20 +565,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             }
                             continue;
                         }
-                    } else if (part_mode) {                      // sum the partial tiles of all CTAs of the cluster (distributed smem)
-                        float s[32];
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) s[j] = 0.f;
-                        for (int r = 0; r < csk; ++r) {
-                            const uint32_t ra = map_to_cta(base + part_off, static_cast<uint32_t>(r));
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 t4 = ld_dsmem_v4(ra + ((j ^ (lane & 7)) << 4));
-                                s[4 * j] += t4.x; s[4 * j + 1] += t4.y; s[4 * j + 2] += t4.z; s[4 * j + 3] += t4.w;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(s[j]);
                     } else {                                     // finaliser: read the complete sums back (L2) and clear them
                         if (row_ok && nb + 32 <= p.n_valid) {
 #pragma unroll
@@ -716,7 +677,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 }
             }       // items
             }       // pass
-            if (csk > 1) cluster_sync_all();                         // peers may still be reading this CTA's partial tile
         }           // tiles
         if (p.stats && !(p.dbg & 2)) flush_stats();
         if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
