@@ -35,6 +35,7 @@ _SIGS = {
     "sr3_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sr3_p_mean_variance": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(c_float), c_void_p]),
     "sr3_p_sample": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]),
+    "sr3_p_losses": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(c_double), c_void_p]),
     "sr3_p_sample_loop": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p, c_int,
                                   POINTER(c_int), c_void_p]),
     "sr3_super_resolution_host": (c_int, [c_void_p, c_void_p, c_void_p, c_uint64, c_uint64, c_void_p, c_void_p]),
@@ -198,6 +199,15 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(lib().sr3_p_sample(self._h, _ptr(x), _ptr(c), int(t), _ptr(n), int(seed), int(first_index), _ptr(out), _stream()))
         return out
+
+    def p_losses(self, hr, sr, gamma, noise, loss_type="l1"):
+        hr, noise = _f32c(hr, self.device), _f32c(noise, self.device)
+        s = None if sr is None else _f32c(sr, self.device)
+        g = _f32c(gamma, self.device).reshape(-1)
+        out = c_double()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_p_losses(self._h, _ptr(hr), _ptr(s), _ptr(g), _ptr(noise), 1 if loss_type == "l1" else 2, ctypes.byref(out), _stream()))
+        return out.value
 
     def p_sample_loop(self, condition_x, x_T, noises=None, seed=0, first_index=0, want_snapshots=True):
         c = None if condition_x is None else _f32c(condition_x, self.device)

@@ -317,4 +317,42 @@ __global__ void __launch_bounds__(256) load_nchw_kernel(const float* __restrict_
     }
 }
 
+// q_sample (diffusion.py:212-219) fused with the input load: x_noisy = g * x0 + sqrt(1 - g^2) * noise, written as bf16 into the
+// UNet input buffer (channels [coff, coff+C)); g = continuous_sqrt_alpha_cumprod of the image.
+__global__ void __launch_bounds__(256) q_sample_load_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ gamma,
+                                                            int B, int C, int H, int W, __nv_bfloat16* __restrict__ in_buf, int in_C, int coff) {
+    const long long total = static_cast<long long>(B) * C * H * W;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        long long r = i;
+        const int w = static_cast<int>(r % W); r /= W;
+        const int h = static_cast<int>(r % H); r /= H;
+        const int c = static_cast<int>(r % C);
+        const int b = static_cast<int>(r / C);
+        const float g = gamma[b];
+        const float v = __fadd_rn(__fmul_rn(g, x0[i]), __fmul_rn(sqrtf(__fsub_rn(1.0f, __fmul_rn(g, g))), noise[i]));
+        in_buf[((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c] = __float2bfloat16_rn(v);
+    }
+}
+
+// L1Loss / MSELoss with reduction='sum' (diffusion.py:84-90, 245): loss += sum |noise - eps| (or squared), double accumulation
+__global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__ noise, const float* __restrict__ eps, long long n, int l2,
+                                                       double* __restrict__ out) {
+    double acc = 0.0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float d = noise[i] - eps[i];
+        acc += l2 ? static_cast<double>(d) * d : static_cast<double>(fabsf(d));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    __shared__ double ws[8];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += ws[i];
+        atomicAdd(out, t);
+    }
+}
+
 }  // namespace sr3

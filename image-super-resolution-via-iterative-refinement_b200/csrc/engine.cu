@@ -479,6 +479,7 @@ struct sr3_engine {
     float *nl_table = nullptr, *post_tab = nullptr;
     int T = 0, T_cap = 0;
     std::vector<float> logvar_host;
+    double* loss_dev = nullptr;
     float *tau = nullptr, *film = nullptr, *film_w = nullptr, *film_b = nullptr, *film_cb = nullptr;
     float *mlp_w1 = nullptr, *mlp_b1 = nullptr, *mlp_w2 = nullptr, *mlp_b2 = nullptr;
     int F = 0;
@@ -1157,6 +1158,32 @@ int sr3_p_sample(sr3_engine* e, const float* x, const float* cond, int t, const 
     e->push_ctl(st);
     e->run_step(st);
     CK(cudaMemcpyAsync(x_prev, e->x_state, e->img_bytes(), cudaMemcpyDeviceToDevice, st));
+    API_END
+}
+
+int sr3_p_losses(sr3_engine* e, const float* hr, const float* sr, const float* gamma, const float* noise, int loss_type, double* loss_host,
+                 void* stream) {
+    API_BEGIN
+    REQUIRE(e && hr && gamma && noise && loss_host, "null argument");
+    REQUIRE(loss_type == 1 || loss_type == 2, "loss_type must be 1 (l1) or 2 (l2)");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CK(cudaSetDevice(e->dev));
+    if (e->cfg.conditional) { REQUIRE(sr != nullptr, "x_in['SR'] is required by a conditional model"); e->load_nchw(sr, e->cond_c, 0, nullptr, st); }
+    const long long total = 1LL * e->B * e->cfg.channels * e->H * e->W;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    q_sample_load_kernel<<<blocks, 256, 0, st>>>(hr, noise, gamma, e->B, e->cfg.channels, e->H, e->W, e->in_buf, e->in_C, e->cond_c);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(e->nl_buf, gamma, e->B * 4, cudaMemcpyDeviceToDevice, st));
+    StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
+    c.nl_from_table = 0; c.out_mode = 0; c.t_next = 0;
+    e->push_ctl(st);
+    e->run_step(st);
+    if (!e->loss_dev) e->loss_dev = static_cast<double*>(e->mem.alloc(sizeof(double)));
+    CK(cudaMemsetAsync(e->loss_dev, 0, sizeof(double), st));
+    loss_sum_kernel<<<blocks, 256, 0, st>>>(noise, e->eps_buf, total, loss_type == 2 ? 1 : 0, e->loss_dev);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(loss_host, e->loss_dev, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
     API_END
 }
 

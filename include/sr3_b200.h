@@ -78,6 +78,13 @@ int sr3_p_mean_variance(sr3_engine* e, const float* x, const float* condition_x,
 int sr3_p_sample(sr3_engine* e, const float* x, const float* condition_x, int t, const float* noise, uint64_t seed,
                  uint64_t first_sample_index, float* x_prev, void* stream);
 
+/* p_losses forward (diffusion.py:221-246) with the random draws injected: hr = x_in['HR'] [B,3,H,W], sr = x_in['SR'] (NULL when
+ * unconditional), gamma [B] = continuous_sqrt_alpha_cumprod, noise [B,3,H,W] (all DEVICE fp32).  q_sample (diffusion.py:212-219),
+ * the UNet and the summed L1 (loss_type 1) / L2 (2) loss (diffusion.py:84-90) run natively; *loss_host receives the scalar.
+ * Forward value only: the backward pass is not implemented. */
+int sr3_p_losses(sr3_engine* e, const float* hr, const float* sr, const float* gamma, const float* noise, int loss_type, double* loss_host,
+                 void* stream);
+
 /* p_sample_loop / super_resolution / sample (diffusion.py:176-210): runs t = T-1 .. 0 as T launches of one captured CUDA
  * graph.  x_T: DEVICE [B,3,H,W] initial noise (the reference's torch.randn(shape)).  noises: optional DEVICE
  * [T][B,3,H,W], noises[i] used at step i.  Every (i % (1|T/10) == 0) the image is appended to `snapshots`
