@@ -379,17 +379,37 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
     for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh != 0) has3 = true; }
     tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
     if (tall_ok) {
-        d.tall = 1; d.mh = 2; d.w_box = 8;
-        if (OH >= 32) { d.h_box = 32; d.b_box = 1; d.a_box_w = 8; d.a_box_h = 34; d.a_box_b = 1; d.a_half_off = 16 * 1024; }
-        else { d.h_box = 16; d.b_box = 2; d.a_box_w = 8; d.a_box_h = 18; d.a_box_b = 2; d.a_half_off = 18 * 1024; }
-        int bn = cout % 128 == 0 ? 128 : (cout % 64 == 0 ? 64 : 16);
-        if (bn == 128) {      // keep every SM busy: fall back to 64-wide tiles when 128-wide ones would leave SMs idle
-            const long long tiles128 = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box) * (cout / 128);
-            if (tiles128 < 100) bn = 64;
+        // tile shape: the most ingest-efficient (256 rows x 128 columns) that still gives ~a wave of tiles; small batches / low
+        // resolutions fall back to smaller tiles so that more SMs stream K concurrently (each CTA's K loop is latency bound)
+        d.tall = 1; d.w_box = 8;
+        struct Cand { int mh, bn; };
+        const Cand cands[4] = {{2, 128}, {2, 64}, {1, 64}, {1, 32}};
+        auto geom = [&](int mh, int& h_box, int& b_box) {
+            if (mh == 2 && OH >= 32) { h_box = 32; b_box = 1; }
+            else if (mh == 2) { h_box = 16; b_box = 2; }
+            else { h_box = 16; b_box = 1; }
+        };
+        int pick = -1;
+        long long best_tiles = -1; int best = -1;
+        for (int i = 0; i < 4; ++i) {
+            const Cand& c = cands[i];
+            if (cout % c.bn != 0) continue;
+            if (c.bn == 128 && has_resid) continue;   // residual staging (8 warps x 8 KB) would leave room for a single 84 KB stage
+            int hb, bb; geom(c.mh, hb, bb);
+            const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn);
+            if (tiles > best_tiles) { best_tiles = tiles; best = i; }
+            if (tiles >= 100) { pick = i; break; }
         }
-        if (bn == 128 && has_resid) bn = 64;   // residual staging (8 warps x 8 KB) would leave room for a single 84 KB stage
-        if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 64 || v == 128) && cout % v == 0) bn = v; }
-        d.block_n = bn;
+        int mh = 2, bn = 16;                          // Cout = 3 (final conv) keeps the 16-wide tile
+        if (cout % 32 == 0) { const int i = pick >= 0 ? pick : best; mh = cands[i].mh; bn = cands[i].bn; }
+        if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && cout % v == 0) bn = v; }
+        if (const char* e = getenv("SR3_TALL_MH")) { int v = atoi(e); if (v == 1 || v == 2) mh = v; }
+        d.mh = mh; d.block_n = bn;
+        geom(mh, d.h_box, d.b_box);
+        d.a_box_w = 8; d.a_box_h = d.h_box / (mh == 2 && d.b_box == 1 ? 1 : 1) + 2; d.a_box_b = d.b_box;
+        if (mh == 2 && d.b_box == 1) { d.a_box_h = 34; d.a_half_off = 16 * 1024; }
+        else if (mh == 2) { d.a_box_h = 18; d.a_half_off = 18 * 1024; }
+        else { d.a_box_h = 18; d.a_half_off = 0; }
     } else {
         d.tall = 0; d.mh = 1;
         pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);

@@ -9,6 +9,8 @@ CONFIGS = {
     "sr_sr3_16_128 B=16": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.2), 128, True, 16),
     "sr_sr3_64_512 B=4": (dict(in_channel=6, out_channel=3, inner_channel=64, norm_groups=16, channel_multiplier=[1, 2, 4, 8, 16], attn_res=[], res_blocks=1, dropout=0), 512, True, 4),
     "sample_sr3_128 (uncond) B=32": (dict(in_channel=3, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.2), 128, False, 32),
+    "sr_sr3_16_128 B=8 (one of 2 GPUs)": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.2), 128, True, 8),
+    "sr_sr3_16_128 B=4 (one of 4 GPUs)": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.2), 128, True, 4),
     "sr_sr3_16_128 B=2 (one of 8 GPUs)": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.2), 128, True, 2),
 }
 dev = torch.device("cuda", 0)
