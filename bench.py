@@ -1,10 +1,12 @@
 #!/usr/bin/env python
-"""bench.py -- diffusion steps/sec of the SR3 16->128 sampler at global batch 16 (BASELINE.json metric, configs[1]).
+"""bench.py -- diffusion steps/sec of the SR3 16->128 sampler at batch 16 (BASELINE.json metric, configs[1]).
 
     python bench.py --gpus N --steps K --warmup W            # our arm   (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the reference's algorithm on the host cores
 
-A "step" is one reverse-diffusion step (p_sample) applied to the WHOLE global batch: UNet forward + posterior update.
+A "step" is one reverse-diffusion step (p_sample) of a batch of 16 images: UNet forward + posterior update.  With N GPUs the
+images are partitioned (no per-step exchange): --scaling weak (default) gives every GPU its own batch of 16 and `value` sums
+the batch-16 steps of all ranks; --scaling strong shards ONE batch of 16 (16/N images per GPU, latency bound below ~4 images).
 `value`   : K steps of the captured step graph with the sampler state resident in HBM, CUDA events, max over ranks.
 `e2e`     : the same metric through the public API call a user makes (GaussianDiffusion.super_resolution on a HOST
             tensor, schedule length K): H2D of the condition + K steps + D2H of the images (+ all-gather for N>1)
@@ -175,7 +177,7 @@ def run_reference(args, rank, world):
     v = 1.0 / per_step_full
     cores = torch.get_num_threads()
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": per_step_full * 1e3, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "sr_sr3_16_128.json sampling, global batch 16, p_sample on host cores", "global_batch": GLOBAL_BATCH},
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
                              "sample": f"p_sample on {b} of the 16 images per step, time scaled by 16/{b}; {args.steps} steps after {args.warmup} warm-up"},
@@ -191,6 +193,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N>1: weak = every GPU samples its own batch of 16 images (global batch 16N, value in batch-16 steps/s); "
+                         "strong = ONE batch of 16 images sharded over the GPUs")
     ap.add_argument("--profile-out", default=None, help="write the per-launch timing table of one step to this JSON file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -212,16 +217,23 @@ def main():
         os.environ["NCCL_DEBUG"] = os.environ.get("SR3_NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line only)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    assert GLOBAL_BATCH % world == 0
-    per = GLOBAL_BATCH // world
+    # The path partitions by image (no per-step exchange).  Weak scaling (default, tier rule 5): each rank runs the configuration the metric
+    # is quoted on (16 images); `value` counts batch-16 steps of ALL ranks.  Strong scaling shards one batch of 16.
+    weak = args.scaling == "weak"
+    if weak:
+        per, global_batch = GLOBAL_BATCH, GLOBAL_BATCH * world
+    else:
+        assert GLOBAL_BATCH % world == 0
+        per, global_batch = GLOBAL_BATCH // world, GLOBAL_BATCH
+    units = global_batch / GLOBAL_BATCH          # batch-16 steps done per reverse step of the whole job
 
     torch.manual_seed(0)
     net = sr3_b200.define_G(make_opt(SCHED)).to(dev)
     net.set_new_noise_schedule(SCHED, dev)
     net.eval()
     g = torch.Generator().manual_seed(0)
-    cond_all = torch.rand(GLOBAL_BATCH, 3, IMAGE, IMAGE, generator=g) * 2 - 1
-    xT_all = torch.randn(GLOBAL_BATCH, 3, IMAGE, IMAGE, generator=g)
+    cond_all = torch.rand(global_batch, 3, IMAGE, IMAGE, generator=g) * 2 - 1
+    xT_all = torch.randn(global_batch, 3, IMAGE, IMAGE, generator=g)
     lo = rank * per
     cond_h = cond_all[lo:lo + per].contiguous().pin_memory()
     xT_h = xT_all[lo:lo + per].contiguous().pin_memory()
@@ -256,13 +268,13 @@ def main():
     ms = float(t_ms.item())
     state = eng.read_state()
     assert torch.isfinite(state).all(), "sampler state is not finite"
-    value = K / (ms * 1e-3)
+    value = units * K / (ms * 1e-3)
 
     # ---------------- end to end through the public API on host tensors: `e2e`
     schedK = dict(SCHED, n_timestep=K)
     net.set_new_noise_schedule(schedK, dev)
     out_h = None
-    gathered = torch.empty(GLOBAL_BATCH, 3, IMAGE, IMAGE, device=dev) if world > 1 else None
+    gathered = torch.empty(global_batch, 3, IMAGE, IMAGE, device=dev) if world > 1 else None
     e2e_s = []
     for it in range(4):                      # first pass warms the allocator / graph for this schedule; median of the other three
         barrier()
@@ -275,7 +287,7 @@ def main():
     e2e_t = torch.tensor([sorted(e2e_s[1:])[1]], device=dev)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = K / float(e2e_t.item())
+    e2e_val = units * K / float(e2e_t.item())
     img_bytes = per * 3 * IMAGE * IMAGE * 4
     net.set_new_noise_schedule(SCHED, dev)
 
@@ -319,9 +331,11 @@ def main():
                "sample": f"oracle p_sample on {b} of 16 images, 3 steps after 1 warm-up, time scaled by 16/{b}"}
 
     line = {"metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "sr_sr3_16_128.json sampling (configs[1]): global batch 16, T=2000 linear schedule, random-init weights",
-                       "global_batch": GLOBAL_BATCH, "per_gpu_batch": per, "parallelism": f"batch-sharded x{world}, no per-step collective",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "sr_sr3_16_128.json sampling (configs[1]): batch 16 per GPU, T=2000 linear schedule, random-init weights" if weak else
+                                   "sr_sr3_16_128.json sampling (configs[1]): ONE batch of 16 sharded over the GPUs, T=2000 linear schedule, random-init weights",
+                       "global_batch": global_batch, "per_gpu_batch": per, "parallelism": f"batch-sharded x{world}, no per-step collective",
+                       "value_unit_note": "steps/s of batch-16 work: (images x reverse steps per second) / 16, summed over all ranks",
                        "l2": "per-step working set (~%.1f GB of activations+weights) exceeds the 126 MB L2; no explicit flush" % (eng.workspace_bytes() / 2 ** 30),
                        "image_steps_per_s": value * GLOBAL_BATCH},
             "e2e": {"value": e2e_val, "unit": "steps/s", "h2d_bytes_per_step": 2 * img_bytes / K, "d2h_bytes_per_step": img_bytes / K,

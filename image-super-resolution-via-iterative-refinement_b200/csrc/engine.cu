@@ -318,25 +318,22 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     } else {
         p.out_map = p.b_map; p.res_map = p.b_map;
     }
-    // split-K: when the output has too few tiles to occupy the SMs, several CTAs share a tile and each streams a slice of K
+    // split-K: when the output has too few tiles to occupy the SMs, `ksplit` CTAs share a tile, each streams a slice of K and parks its
+    // partial tile in `ws`; every one of them then finalises a 1/ksplit share of the tile (gemm_tcgen05.cuh, epilogue pass 1).
+    // One (tile, split) pair per SM at most: all CTAs are co-resident, which the in-kernel wait relies on.
     p.ksplit = 1;
     {
         const int tiles = d.tiles_w * d.tiles_h * d.tiles_b * d.n_tiles * d.nz;
-        int ks = d.ksplit_max;
-        if (const char* e = getenv("SR3_KSPLIT")) ks = atoi(e);
+        const int ks = d.ksplit_max;
         if (ks > 1 && d.mode == 0 && d.out_f32 && d.block_n >= 32 && d.n_valid % 32 == 0) {
             int want = num_sms() / tiles;                  // CTAs per tile that still fit one wave
             if (want > ks) want = ks;
             if (want > p.num_k / 2) want = p.num_k / 2;    // at least two stages per slice
+            const int units = d.mh * (d.block_n / 32) * 4; // 32x32 units of a tile: every split finalises at least one
+            if (want > units) want = units;
             if (want > 1) {
                 p.ksplit = want;
-                size_t elems = 0;                          // workspace with the addressing of out_f32
-                {
-                    const OutSpec& o = d.os;
-                    elems = (size_t)(o.off + (long long)(d.nz - 1) * o.sZ + (long long)(d.tiles_b * d.b_box - 1) * o.sB + (long long)(d.OH - 1) * o.sH +
-                                     (long long)(d.OW - 1) * o.sW + d.n_valid);
-                }
-                p.ws = static_cast<float*>(mem.alloc(elems * sizeof(float)));
+                p.ws = static_cast<float*>(mem.alloc((size_t)tiles * want * d.mh * 128 * d.block_n * sizeof(float), false));
                 p.counters = static_cast<unsigned int*>(mem.alloc((size_t)tiles * sizeof(unsigned int)));
             }
         }
@@ -374,13 +371,36 @@ void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box);
 int pick_block_n(int cout);
 
 // Geometry of an image conv: the "tall halo" form for 3x3 stride-1 convs at >= 16x16, else a plain 128-pixel patch per tap.
+// The tile shape (rows x BLOCK_N) and the split-K factor are chosen by a byte model of the per-CTA critical path: a CTA ingests
+// stages x (A box + B boxes) through TMA at a fixed ~47 B/clk, runs ceil(tiles * split / SMs) waves, and a split tile costs an extra
+// partial-tile store + reload + a grid-level handshake.  (Measured on B200: tools/gpu_splitk_sweep.py)
 void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid = false) {
     bool tall_ok = getenv("SR3_NO_TALL") == nullptr && OW >= 8 && OH >= 16, has3 = false;
     for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh != 0) has3 = true; }
     tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
+    const bool allow_split = getenv("SR3_NO_KSPLIT") == nullptr;
+    const int sms = num_sms();
+    // cost in bytes of the slowest CTA; `split` returns the factor the cost was computed for
+    auto model = [&](long long tiles, int nstage, long long stage_bytes, int rows, int bn, int& split) -> double {
+        int smax = 1;
+        if (allow_split && bn >= 32 && cout % 32 == 0) {
+            smax = (int)(sms / tiles);
+            const int units = (rows / 128) * (bn / 32) * 4;
+            if (smax > units) smax = units;
+            if (smax > nstage / 2) smax = nstage / 2;
+            if (smax > 16) smax = 16;
+            if (smax < 1) smax = 1;
+        }
+        split = smax;
+        const long long waves = (tiles * smax + sms - 1) / sms;
+        double c = (double)waves * ((nstage + smax - 1) / smax) * (double)stage_bytes;
+        // a split tile: partial tile out (TMEM -> registers -> L2) and back, weighted 2x against streamed TMA bytes, plus ~1.4 us of
+        // grid-level handshake; a residual is then read with plain loads instead of TMA
+        if (smax > 1) c += 4.0 * rows * bn * 4 + 131072.0 + (has_resid ? 2.0 * rows * bn * 4 : 0.0);
+        return c;
+    };
+    d.ksplit_max = 1;
     if (tall_ok) {
-        // tile shape: the most ingest-efficient (256 rows x 128 columns) that still gives ~a wave of tiles; small batches / low
-        // resolutions fall back to smaller tiles so that more SMs stream K concurrently (each CTA's K loop is latency bound)
         d.tall = 1; d.w_box = 8;
         struct Cand { int mh, bn; };
         const Cand cands[4] = {{2, 128}, {2, 64}, {1, 64}, {1, 32}};
@@ -389,24 +409,36 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
             else if (mh == 2) { h_box = 16; b_box = 2; }
             else { h_box = 16; b_box = 1; }
         };
-        int pick = -1;
-        long long best_tiles = -1; int best = -1;
-        for (int i = 0; i < 4; ++i) {
-            const Cand& c = cands[i];
-            if (cout % c.bn != 0) continue;
-            if (c.bn == 128 && has_resid) continue;   // residual staging (8 warps x 8 KB) would leave room for a single 84 KB stage
-            int hb, bb; geom(c.mh, hb, bb);
-            const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn);
-            if (tiles > best_tiles) { best_tiles = tiles; best = i; }
-            if (tiles >= 100) { pick = i; break; }
+        // stages per tile: one per (source, 64-channel chunk, dw) group of vertical taps
+        int nstage = 0;
+        for (size_t i = 0; i < d.slabs.size(); ++i) {
+            bool first = true;
+            for (size_t j = 0; j < i; ++j)
+                if (d.slabs[j].a_sel == d.slabs[i].a_sel && d.slabs[j].a_chan == d.slabs[i].a_chan && d.slabs[j].dw == d.slabs[i].dw) { first = false; break; }
+            if (first) ++nstage;
         }
-        int mh = 2, bn = 16;                          // Cout = 3 (final conv) keeps the 16-wide tile
-        if (cout % 32 == 0) { const int i = pick >= 0 ? pick : best; mh = cands[i].mh; bn = cands[i].bn; }
-        if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && cout % v == 0) bn = v; }
-        if (const char* e = getenv("SR3_TALL_MH")) { int v = atoi(e); if (v == 1 || v == 2) mh = v; }
-        d.mh = mh; d.block_n = bn;
+        int mh = 2, bn = 16, split = 1;               // Cout = 3 (final conv) keeps the 16-wide tile
+        if (cout % 32 == 0) {
+            double best = 1e300;
+            for (int i = 0; i < 4; ++i) {
+                const Cand& c = cands[i];
+                if (cout % c.bn != 0) continue;
+                int hb, bb; geom(c.mh, hb, bb);
+                const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn);
+                const long long stage_bytes = (c.mh == 2 ? 36864 : 18432) + 3ll * c.bn * 128;
+                int sp = 1;
+                const double cost = model(tiles, nstage, stage_bytes, c.mh * 128, c.bn, sp);
+                // the residual is staged through smem (8 warps x 8 KB) unless the tile is split: a 256x128 tile would be left with one stage
+                if (c.bn == 128 && has_resid && sp <= 1) continue;
+                if (cost < best) { best = cost; mh = c.mh; bn = c.bn; split = sp; }
+            }
+        }
+        if (const char* e = getenv("SR3_TALL_BN")) { int v = atoi(e); if ((v == 32 || v == 64 || v == 128) && cout % v == 0) { bn = v; split = 16; } }
+        if (const char* e = getenv("SR3_TALL_MH")) { int v = atoi(e); if (v == 1 || v == 2) { mh = v; split = 16; } }
+        if (mh == 2 && bn == 32) bn = 64;
+        d.mh = mh; d.block_n = bn; d.ksplit_max = allow_split ? split : 1;
         geom(mh, d.h_box, d.b_box);
-        d.a_box_w = 8; d.a_box_h = d.h_box / (mh == 2 && d.b_box == 1 ? 1 : 1) + 2; d.a_box_b = d.b_box;
+        d.a_box_w = 8; d.a_box_b = d.b_box;
         if (mh == 2 && d.b_box == 1) { d.a_box_h = 34; d.a_half_off = 16 * 1024; }
         else if (mh == 2) { d.a_box_h = 18; d.a_half_off = 18 * 1024; }
         else { d.a_box_h = 18; d.a_half_off = 0; }
@@ -414,14 +446,21 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
         d.tall = 0; d.mh = 1;
         pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
         d.block_n = pick_block_n(cout);
-        // few output pixels (8x8 levels): 32-wide tiles put every SM to work.  (Split-K -- SR3_KSPLIT=n, wide tiles -- is implemented and
-        // tested but measured slower here: 3.91 vs 3.57 ms/step at B=16, 2.65 vs 2.30 at B=2; the fp32 red.add traffic and the serial
-        // finalising CTA cost more than the shorter K loops save.)
         const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box);
-        if (getenv("SR3_KSPLIT") == nullptr && getenv("SR3_BLOCK_N") == nullptr && d.block_n == 128 && cout % 32 == 0 && mt * (cout / 128) < 64)
-            d.block_n = (mt * (cout / 64) >= 100) ? 64 : 32;
+        if (getenv("SR3_BLOCK_N") == nullptr && cout % 32 == 0) {
+            // generic stages group up to three K slabs (one A box + one B box each)
+            const int nstage = ((int)d.slabs.size() + 2) / 3;
+            double best = 1e300;
+            for (int bn = 128; bn >= 32; bn >>= 1) {
+                if (cout % bn != 0) continue;
+                int sp = 1;
+                const double cost = model(mt * (cout / bn), nstage, 3ll * (16384 + bn * 128), 128, bn, sp);
+                if (bn == 128 && sp > 1) continue;      // 96 KB stages leave a 2-deep pipeline: measured slower than 64-wide split tiles
+                if (cost < best) { best = cost; d.block_n = bn; d.ksplit_max = sp; }
+            }
+        }
     }
-    d.ksplit_max = getenv("SR3_KSPLIT") ? 8 : 1;
+    if (const char* e = getenv("SR3_KSPLIT")) d.ksplit_max = atoi(e);
     d.tiles_w = OW / d.w_box; d.tiles_h = OH / d.h_box; d.tiles_b = Bp / d.b_box;
 }
 
@@ -433,7 +472,7 @@ void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box) {
 }
 
 int pick_block_n(int cout) {
-    if (const char* e = getenv("SR3_BLOCK_N")) { int v = atoi(e); if (v == 64 || v == 128 || v == 256) if (cout % v == 0) return v; }
+    if (const char* e = getenv("SR3_BLOCK_N")) { int v = atoi(e); if (v == 32 || v == 64 || v == 128 || v == 256) if (cout % v == 0) return v; }
     if (cout % 128 == 0) return 128;
     if (cout % 64 == 0) return 64;
     return 16;

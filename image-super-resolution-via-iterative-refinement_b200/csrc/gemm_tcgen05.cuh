@@ -92,7 +92,7 @@ struct GemmParams {
     int epi_c4_is_z;         // 5th coordinate of out_map / res_map: gemm-batch z (1) or image index (0)
     int ksplit;              // split-K factor: ksplit CTAs share one output tile, partial sums meet in `ws` (fp32, same addressing as out_f32)
     float* ws;               // zero between launches (the finalising CTA clears what it reads)
-    unsigned int* counters;  // [tiles] arrival counters, self resetting
+    unsigned int* counters;  // [tiles] arrival counters (monotonic: +ksplit per launch)
     const void* pf_ptr;      // weights of the NEXT tile-kernel launch: pulled into L2 while this launch runs (they would otherwise be
     long long pf_bytes;      // first-touch HBM reads on the critical path of every pipeline stage of that launch)
     int dbg;                 // SR3_DBG bit mask (timing experiments only): 1 skip epilogue body, 2 skip stats, 4 skip out store,
@@ -245,7 +245,6 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
     auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };   // w in [0, 8)
     uint8_t* aux_ptr = base_ptr + stages * stage_bytes + epi_bytes;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS));
-    volatile uint32_t* split_flag = tmem_slot + 1;
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
     StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
     float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + ((p.num_k * 96 + 127) / 128) * 128);
@@ -429,9 +428,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             decode(tile, w0, h0, b0, n0, z);
             const int acc = ti & 1;
             // geometry of a work item: rows of `half`, columns of `ch`
-            auto item_geom = [&](int item, int& half, int& ch, int& sw, int& sh, int& c4) {
+            auto item_geom = [&](int item, int qq, int& half, int& ch, int& sw, int& sh, int& c4) {
                 half = item / NCH; ch = item % NCH;
-                const int r0 = half * 128 + q * 32;
+                const int r0 = half * 128 + qq * 32;
                 sw = r0 % p.w_box;
                 sh = (r0 / p.w_box) % p.h_box;
                 const int sb = r0 / (p.w_box * p.h_box);
@@ -439,7 +438,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             };
             auto request_resid = [&](int item) {                   // lane 0 only
                 int half, ch, sw, sh, c4;
-                item_geom(item, half, ch, sw, sh, c4);
+                item_geom(item, q, half, ch, sw, sh, c4);
                 const uint32_t b = res_count & 1;
                 mbar_arrive_expect_tx(res_bar(ew, b), 4096);
                 tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(ew, b), n0 + ch * 32, w0 + sw, 0, h0 + sh, c4);
@@ -475,37 +474,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar(acc));
             }
-            // pass 0 reads the accumulator from TMEM.  With split-K it only adds the partial sums into `ws`; the CTA that arrives
-            // last at the tile's counter runs pass 1, which reads the complete sums back and does the real epilogue.
+            // pass 0 reads the accumulator from TMEM.  With split-K it only stores this CTA's partial tile into its slice of `ws`;
+            // once all `ksplit` CTAs of the output tile have arrived at the tile's counter, pass 1 runs in EVERY one of them on a
+            // 1/ksplit share of the tile's 32x32 units: sum the partials (fixed order: deterministic) and do the real epilogue.
+            // (All CTAs of the grid are resident -- at most one (tile, split) pair per SM -- so the spin wait cannot deadlock.)
             const int npass = ksplit > 1 ? 2 : 1;
+            const int sp = tile % ksplit;
+            constexpr long long SLICE = static_cast<long long>(MH) * 128 * BLOCK_N;       // floats per partial tile
 #pragma unroll 1
             for (int pass = 0; pass < npass; ++pass) {
             if (pass == 1) {
                 __threadfence();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
                 if (ew == 0 && lane == 0) {
+                    unsigned int* ctr = p.counters + tile / ksplit;
+                    const unsigned int old = atomicAdd(ctr, 1u);
+                    const unsigned int target = (old / ksplit + 1u) * ksplit;              // the counter only ever grows
+                    uint64_t t0 = 0;
+                    for (uint32_t spins = 0;; ++spins) {
+                        unsigned int v;
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                        if (static_cast<int>(v - target) >= 0) break;
+                        if ((spins & 1023u) == 1023u) {
+                            const uint64_t now = globaltimer_ns();
+                            if (t0 == 0) t0 = now;
+                            if (now - t0 > 4000000000ull) {
+                                printf("sr3: split-K wait timeout block=(%d,0,0) tile=%d counter=%u target=%u\n", blockIdx.x, tile, v, target);
+                                __trap();
+                            }
+                        }
+                    }
                     __threadfence();
-                    const unsigned int old = atomicAdd(p.counters + tile / ksplit, 1u);
-                    const bool last = (old == static_cast<unsigned int>(ksplit - 1));
-                    if (last) p.counters[tile / ksplit] = 0u;
-                    __threadfence();
-                    *split_flag = last ? 1u : 0u;
                 }
+                __syncwarp();
                 asm volatile("bar.sync 1, 256;" ::: "memory");
-                const bool is_last = (*split_flag != 0u);
-                asm volatile("bar.sync 1, 256;" ::: "memory");       // everyone has read the flag before it can be rewritten
-                if (!is_last) break;
-                __threadfence();
             }
             const bool from_ws = (pass == 1);
             const bool to_ws = (ksplit > 1 && pass == 0);
-            if (has_work)
+            // iteration space: pass 0 / no split -- this warp's (half, chunk) items of its own TMEM lane quadrant;
+            // pass 1 -- units u = item * 4 + quadrant with u % ksplit == sp, dealt round-robin to the eight warps
+            const int it0 = from_ws ? sp + ksplit * ew : grp;
+            const int itn = from_ws ? NITEMS * 4 : (has_work ? NITEMS : 0);
+            const int its = from_ws ? ksplit * GEMM_EPI_WARPS : 2;
 #pragma unroll 1
-            for (int item = grp; item < NITEMS; item += 2) {
+            for (int it = it0; it < itn; it += its) {
+                const int item = from_ws ? (it >> 2) : it;
+                const int qq = from_ws ? (it & 3) : q;
                 int half, ch, sw, sh, c4;
-                item_geom(item, half, ch, sw, sh, c4);
-                const bool last_item = (item + 2 >= NITEMS);
-                const int row = half * 128 + q * 32 + lane;
+                item_geom(item, qq, half, ch, sw, sh, c4);
+                const bool last_item = !from_ws && (item + 2 >= NITEMS);
+                const int row = half * 128 + qq * 32 + lane;
                 const int w = row % p.w_box;
                 const int h = (row / p.w_box) % p.h_box;
                 const int bb = row / (p.w_box * p.h_box);
@@ -534,10 +552,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 } else {
                     const int nb = n0 + ch * 32;
                     float bv = 0.f;
+                    if (from_ws) {
+                        const int n = nb + lane;
+                        if (n < p.n_valid) {
+                            if (p.bias) bv += __ldg(&p.bias[n]);
+                            if (p.bias2) {
+                                const int img0 = b0 + (half * 128 + qq * 32) / (p.w_box * p.h_box);
+                                bv += __ldg(&p.bias2[static_cast<long long>(img0 < p.OB ? img0 : 0) * p.bias2_stride + n]);
+                            }
+                        }
+                    } else {
 #pragma unroll
-                    for (int ii = 0; ii < MAXI; ++ii)
-                        if (item == grp + 2 * ii) bv = bvs[ii];
-                    float* bs = bias_s + (ew * 2 + ((item >> 1) & 1)) * 32;
+                        for (int ii = 0; ii < MAXI; ++ii)
+                            if (item == grp + 2 * ii) bv = bvs[ii];
+                    }
+                    float* bs = bias_s + (ew * 2 + ((from_ws ? (it / its) : (item >> 1)) & 1)) * 32;
                     bs[lane] = bv;
                     __syncwarp();
                     if (use_res_tma) {
@@ -545,7 +574,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         if (!last_item && lane == 0) request_resid(item + 2);   // other buffer: freed one item ago
                     }
                     uint32_t v[32];
-                    const long long wso = (ksplit > 1) ? out_index(p.os, z, img, oh, ow) + nb : 0;
+                    // this thread's eight float4 inside a partial tile: laid out [chunk][j][row] so that the 32 lanes (consecutive rows)
+                    // of one store / load instruction touch 512 contiguous bytes
+                    const long long wrow = (static_cast<long long>(ch) * 8 * (MH * 128) + row) * 4;
+                    constexpr int WJ = MH * 128;                  // float4 stride between the j-th and (j+1)-th quad of a row
                     if (!from_ws) {
                         tmem_ld_32x32(t_acc + ch * 32, v);
                         tmem_ld_wait();
@@ -554,32 +586,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             __syncwarp();
                             if (lane == 0) mbar_arrive(tempty_bar(acc));
                         }
-                        if (to_ws) {                             // split-K: add the scaled partial sums into the shared fp32 tile
-                            if (row_ok && nb + 32 <= p.n_valid) {
+                        if (to_ws) {                             // split-K: park the partial sums
+                            float4* dst = reinterpret_cast<float4*>(p.ws + static_cast<long long>(tile) * SLICE + wrow);
 #pragma unroll
-                                for (int j = 0; j < 8; ++j)
-                                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p.ws + wso + 4 * j),
-                                                 "f"(__uint_as_float(v[4 * j]) * p.scale), "f"(__uint_as_float(v[4 * j + 1]) * p.scale),
-                                                 "f"(__uint_as_float(v[4 * j + 2]) * p.scale), "f"(__uint_as_float(v[4 * j + 3]) * p.scale)
-                                                 : "memory");
-                            }
+                            for (int j = 0; j < 8; ++j)
+                                __stcg(dst + j * WJ, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                                            __uint_as_float(v[4 * j + 3])));
                             continue;
                         }
-                    } else {                                     // finaliser: read the complete sums back (L2) and clear them
-                        if (row_ok && nb + 32 <= p.n_valid) {
+                    } else {                                     // sum the ksplit partial tiles (L2 resident), split 0 first
+                        float acc_f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc_f[j] = 0.f;
+                        const float* src0 = p.ws + static_cast<long long>(tile - sp) * SLICE + wrow;
+                        for (int s2 = 0; s2 < ksplit; ++s2) {
+                            const float4* src = reinterpret_cast<const float4*>(src0 + s2 * SLICE);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                const float4 r = __ldcg(reinterpret_cast<const float4*>(p.ws + wso) + j);
-                                v[4 * j] = __float_as_uint(r.x); v[4 * j + 1] = __float_as_uint(r.y);
-                                v[4 * j + 2] = __float_as_uint(r.z); v[4 * j + 3] = __float_as_uint(r.w);
-                                __stcg(reinterpret_cast<float4*>(p.ws + wso) + j, make_float4(0.f, 0.f, 0.f, 0.f));
+                                const float4 r = __ldcg(src + j * WJ);
+                                acc_f[4 * j] += r.x; acc_f[4 * j + 1] += r.y; acc_f[4 * j + 2] += r.z; acc_f[4 * j + 3] += r.w;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) v[j] = 0u;
                         }
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc_f[j]);
                     }
-                    const float ep_scale = from_ws ? 1.0f : p.scale;
+                    const float ep_scale = p.scale;
                     if (p.dbg & 1) {
                         if (use_res_tma) {
                             const uint32_t b = (res_count - 1) & 1;

@@ -19,4 +19,10 @@ for shape in ("hi64", "hi128", "mid128", "mid256", "lo16", "lo512"):
     run("graph: default", shape)
     run("graph: no-work (dbg57)", shape, {"SR3_DBG": 57})
     run("graph: no epi body (dbg1)", shape, {"SR3_DBG": 1})
-    run("graph: default NO_PDL", shape, {"SR3_NO_PDL": 1})
+    run("graph: skip stats (dbg2)", shape, {"SR3_DBG": 2})
+    run("graph: skip out store (dbg4)", shape, {"SR3_DBG": 4})
+    run("graph: skip stats+store (dbg6)", shape, {"SR3_DBG": 6})
+    run("graph: no loads (dbg24)", shape, {"SR3_DBG": 24})
+    run("graph: no MMA, no epi body (dbg33)", shape, {"SR3_DBG": 33})
+    run("graph: resid", shape, resid=True)
+    run("graph: no stats arg", shape, stats=False)
