@@ -693,14 +693,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         }
                     }
                     if (p.stats && !(p.dbg & 2)) {
-                        float s2[32];
+                        float cs, cq;
+                        if (use_out_tma && !(p.dbg & 4)) {
+                            // the 32x32 tile sits in the (swizzled) staging buffer: lane c walks down column c -- conflict free, and a
+                            // third of the instructions of the shuffle transposition below
+                            const unsigned int okm = __ballot_sync(0xffffffffu, row_ok);
+                            const uint8_t* colp = out_ptr + ((lane & 3) << 2);
+                            const int cq4 = lane >> 2;
+                            float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float x = row_ok ? f[j] : 0.f;
-                            f[j] = x; s2[j] = x * x;
+                            for (int r = 0; r < 32; r += 2) {
+                                float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4));
+                                float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4));
+                                if (okm != 0xffffffffu) {
+                                    if (!((okm >> r) & 1u)) x0 = 0.f;
+                                    if (!((okm >> (r + 1)) & 1u)) x1 = 0.f;
+                                }
+                                a0 += x0; q0 = fmaf(x0, x0, q0);
+                                a1 += x1; q1 = fmaf(x1, x1, q1);
+                            }
+                            cs = a0 + a1; cq = q0 + q1;
+                        } else {
+                            float s2[32];
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const float x = row_ok ? f[j] : 0.f;
+                                f[j] = x; s2[j] = x * x;
+                            }
+                            cs = warp_column_sums(f);
+                            cq = warp_column_sums(s2);
                         }
-                        const float cs = warp_column_sums(f);
-                        const float cq = warp_column_sums(s2);
 #pragma unroll
                         for (int c = 0; c < NCHS; ++c)
                             if (c == ch) { st_sum[c] += cs; st_sq[c] += cq; }
