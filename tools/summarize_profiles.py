@@ -61,5 +61,35 @@ def full(src, dst, note):
         f.write("\nColumns: " + ", ".join(f"`{c}`" for c in cols) + "\n")
 
 
+def metrics(src, dst, note):
+    """Per-launch metric CSV of the tile kernel (one eager step) -> markdown table + profiles/<prefix>_traffic.json."""
+    import json
+    import os
+    lines = [l for l in open(src) if not l.startswith("==")]
+    per = collections.OrderedDict()
+    for r in csv.DictReader(lines):
+        d = per.setdefault(int(r["ID"]), {"name": re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", ""), "grid": r["Grid Size"]})
+        try:
+            d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
+        except ValueError:
+            d[r["Metric Name"]] = None
+    rows = list(per.values())
+    rd = sum(r.get("dram__bytes_read.sum") or 0 for r in rows)
+    wr = sum(r.get("dram__bytes_write.sum") or 0 for r in rows)
+    tot_us = sum((r.get("gpu__time_duration.sum") or 0) / 1000 for r in rows)
+    with open(dst, "w") as f:
+        f.write(f"# {note}\n\n{len(rows)} launches, sum of durations {tot_us:.0f} us (cold caches per launch); DRAM read {rd / 1e9:.2f} GB + write {wr / 1e9:.2f} GB per step.\n\n")
+        f.write("| # | kernel | grid | us | DRAM rd MB | DRAM wr MB | xbar->SM rd MB | L2 % | DRAM % |\n|---|---|---|---:|---:|---:|---:|---:|---:|\n")
+        for i, r in enumerate(rows):
+            g = lambda k, sc=1.0: ("%.1f" % ((r.get(k) or 0) / sc))
+            f.write(f"| {i} | `{r['name']}` | {r['grid']} | {g('gpu__time_duration.sum', 1e3)} | {g('dram__bytes_read.sum', 1e6)} | {g('dram__bytes_write.sum', 1e6)} | "
+                    f"{g('l1tex__m_xbar2l1tex_read_bytes.sum', 1e6)} | {g('lts__throughput.avg.pct_of_peak_sustained_elapsed')} | {g('gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed')} |\n")
+    tj = os.path.join(os.path.dirname(dst), "r01_traffic.json")
+    json.dump({"gemm_tile_kernel_dram_bytes_per_step": rd + wr, "launches": len(rows),
+               "note": "sum of dram__bytes_read.sum + dram__bytes_write.sum over the tile-kernel launches of one eager reverse step, ncu --clock-control none "
+                       "(caches flushed before every launch), B=16 16->128; per-launch table in " + dst}, open(tj, "w"), indent=1)
+    print(f"{len(rows)} launches, {tot_us:.0f} us, DRAM {(rd + wr) / 1e9:.2f} GB -> {dst}, {tj}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    {"launches": launches, "full": full, "metrics": metrics}[sys.argv[1]](sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
