@@ -245,30 +245,49 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident steps: `value`
-    eng.loop_begin(cond_h.to(dev), xT_h.to(dev), seed=1234, first_index=lo)
     T = SCHED["n_timestep"]
-    eng.steps(T - 1, W)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clk:
+
+    def resident_steps(engine, c_h, x_h, first_index, sampler=None):
+        """K graph-launched reverse steps with the sampler state resident in HBM; CUDA events, max over ranks (ms)."""
+        engine.loop_begin(c_h.to(dev), x_h.to(dev), seed=1234, first_index=first_index)
+        engine.steps(T - 1, W)
         barrier()
-        ev0.record()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
         remaining, t = K, T - 1 - W
         while remaining > 0:                 # restart from T-1 if K is longer than the schedule
             n = min(remaining, t + 1)
-            eng.steps(t, n)
+            engine.steps(t, n)
             remaining -= n
             t = T - 1
-        ev1.record()
+        e1.record()
         barrier()
-    ms = ev0.elapsed_time(ev1)
-    t_ms = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
-    state = eng.read_state()
-    assert torch.isfinite(state).all(), "sampler state is not finite"
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        assert torch.isfinite(engine.read_state()).all(), "sampler state is not finite"
+        return float(t_ms.item())
+
+    with ClockSampler(local) as clk:
+        ms = resident_steps(eng, cond_h, xT_h, lo)
     value = units * K / (ms * 1e-3)
+
+    # the other scaling mode at N > 1, as a supplementary number (same timing rules): weak run -> also time ONE batch of 16 sharded
+    # over the ranks; strong run -> also time 16 images per rank
+    other = None
+    if world > 1:
+        o_per = GLOBAL_BATCH // world if weak else GLOBAL_BATCH
+        o_lo = rank * o_per
+        go = torch.Generator().manual_seed(1)
+        o_cond = (torch.rand(o_per, 3, IMAGE, IMAGE, generator=go) * 2 - 1).pin_memory()
+        o_x = torch.randn(o_per, 3, IMAGE, IMAGE, generator=go).pin_memory()
+        o_eng = net.denoise_fn.engine(o_per, conditional=True, channels=3)
+        o_ms = resident_steps(o_eng, o_cond, o_x, o_lo)
+        o_units = 1.0 if weak else float(world)
+        other = {"scaling": "strong" if weak else "weak", "value": o_units * K / (o_ms * 1e-3), "unit": "steps/s", "ms_per_step": o_ms / K,
+                 "per_gpu_batch": o_per, "global_batch": o_per * world}
+        del o_eng
 
     # ---------------- end to end through the public API on host tensors: `e2e`
     schedK = dict(SCHED, n_timestep=K)
@@ -343,6 +362,8 @@ def main():
                     "calls_s": [round(x, 6) for x in e2e_s[1:]]},
             "gpu_launches": eng.launches_per_step() * K, "launches_per_step": eng.launches_per_step(),
             "clocks": clk.summary(), "roofline": roof, "cpu_baseline": cpu}
+    if other is not None:
+        line["other_scaling_mode"] = other
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
