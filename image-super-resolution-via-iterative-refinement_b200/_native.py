@@ -49,6 +49,7 @@ _SIGS = {
     "sr3_engine_read_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int), c_void_p]),
     "sr3_bench_conv": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "sr3_test_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sr3_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sr3_test_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
 }
@@ -277,6 +278,13 @@ def bench_conv(B, H, W, Cin, Cout, k=3, stride=1, resid=False, stats=True, reps=
     ms = c_float()
     _check(lib().sr3_bench_conv(B, H, W, Cin, Cout, k, stride, int(resid), int(stats), reps, ctypes.byref(ms)))
     return ms.value
+
+
+def test_attention(qk_bf16, vT_bf16, nz, Lt, HW, C):
+    """Fused attention core: qk [nz*Lt, 2C] bf16, vT [nz*C, Lt] bf16 -> O [nz*Lt, C] bf16."""
+    out = torch.empty(nz * Lt, C, device=qk_bf16.device, dtype=torch.bfloat16)
+    _check(lib().sr3_test_attention(_ptr(qk_bf16), _ptr(vT_bf16), _ptr(out), nz, Lt, HW, C, _stream()))
+    return out
 
 
 def test_gemm(a_bf16, b_bf16, block_n):

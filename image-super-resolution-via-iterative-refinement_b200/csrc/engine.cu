@@ -17,6 +17,7 @@
 
 #include "../../include/sr3_b200.h"
 #include "aux_kernels.cuh"
+#include "attn_tcgen05.cuh"
 
 using namespace sr3;
 typedef __nv_bfloat16 bf16;
@@ -365,6 +366,34 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
             default: launch_gemm_bn<256, 1>(p, grid, smem, st); break;
         }
     };
+}
+
+// Fused attention core (attn_tcgen05.cuh): S = q k^T / sqrt(C), softmax, O = P v in one launch.  qk [nz*Lt][2C], vT [nz*C][Lt], out [nz*Lt][C].
+bool attn_fusable(int Lt, int C) { return getenv("SR3_NO_FUSED_ATTN") == nullptr && (Lt == 128 || Lt == 256) && C % 128 == 0 && C >= 128; }
+
+Op make_attn_op(const bf16* qk, const bf16* vT, bf16* out, int nz, int Lt, int HW, int C) {
+    REQUIRE(attn_fusable(Lt, C) && Lt % HW == 0, "attention shape Lt=%d HW=%d C=%d is not supported by the fused kernel", Lt, HW, C);
+    AttnParams p;
+    memset(&p, 0, sizeof(p));
+    {
+        const uint64_t dims[2] = {(uint64_t)2 * C, (uint64_t)nz * Lt};
+        const uint64_t str[1] = {(uint64_t)2 * C * 2};
+        const uint32_t box[2] = {64u, 128u};
+        p.qk_map = encode_map(2, qk, dims, str, box);
+    }
+    {
+        const uint64_t dims[2] = {(uint64_t)Lt, (uint64_t)nz * C};
+        const uint64_t str[1] = {(uint64_t)Lt * 2};
+        const uint32_t box[2] = {64u, 128u};
+        p.vt_map = encode_map(2, vT, dims, str, box);
+    }
+    p.out = out; p.C = C; p.Lt = Lt; p.HW = HW;
+    p.dn = (C % 256 == 0) ? 256 : 128;
+    p.scale_log2e = 1.4426950408889634f / sqrtf((float)C);
+    static bool attr_done = false;
+    if (!attr_done) { CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES)); attr_done = true; }
+    const dim3 grid((Lt / 128) * (C / p.dn), nz, 1);
+    return [p, grid](cudaStream_t st) { launch_k(attn_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM_BYTES, st, p); };
 }
 
 void pick_image_box(int W, int H, int& w_box, int& h_box, int& b_box);
@@ -801,30 +830,36 @@ struct sr3_engine {
             d.out_bf16 = vT; d.hs = OutSpec{(long long)C * Lt, 0, 0, Lt, 0};
             push_gemm(d);
         }
-        {   // S[z] = q k^T / sqrt(C)
-            GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C, 2 * C, (long long)Lt * 2 * C);
-            for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, C + c});
-            d.block_n = 128; d.b_ptr = qk; d.b_K = 2 * C; d.b_rows = (long long)Bp * HW;
-            d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
-            d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = Lt;
-            d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = Lt; d.scale = 1.0f / sqrtf((float)C);
-            d.out_f32 = S; d.os = OutSpec{0, (long long)Lt * Lt, 0, Lt, 0};
-            push_gemm(d);
-        }
-        {
-            const long long rows = (long long)nz * Lt;
-            const int blocks = (int)((rows + 7) / 8);
-            push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW); }, 3, 0, (double)rows * Lt * 6.0);
-        }
-        {   // O[z] = P v : rows = queries, N = head dim, K = keys
-            GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
-            for (int c = 0; c < Lt; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
-            d.block_n = 128; d.b_ptr = vT; d.b_K = Lt; d.b_rows = (long long)nz * C;
-            d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
-            d.n_tiles = C / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = C;
-            d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = C;
-            d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C, 0, C, 0};
-            push_gemm(d);
+        if (attn_fusable(Lt, C)) {
+            // S = q k^T / sqrt(C), softmax over the keys of the same image, O = P v: one launch (attn_tcgen05.cuh)
+            const double fl = 4.0 * nz * (double)Lt * Lt * C;
+            push(make_attn_op(qk, vT, O, nz, Lt, HW, C), 5, fl, (double)nz * Lt * C * 2 * 4);
+        } else {
+            {   // S[z] = q k^T / sqrt(C)
+                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C, 2 * C, (long long)Lt * 2 * C);
+                for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, C + c});
+                d.block_n = 128; d.b_ptr = qk; d.b_K = 2 * C; d.b_rows = (long long)Bp * HW;
+                d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
+                d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = Lt;
+                d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = Lt; d.scale = 1.0f / sqrtf((float)C);
+                d.out_f32 = S; d.os = OutSpec{0, (long long)Lt * Lt, 0, Lt, 0};
+                push_gemm(d);
+            }
+            {
+                const long long rows = (long long)nz * Lt;
+                const int blocks = (int)((rows + 7) / 8);
+                push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW); }, 3, 0, (double)rows * Lt * 6.0);
+            }
+            {   // O[z] = P v : rows = queries, N = head dim, K = keys
+                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
+                for (int c = 0; c < Lt; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
+                d.block_n = 128; d.b_ptr = vT; d.b_K = Lt; d.b_rows = (long long)nz * C;
+                d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
+                d.n_tiles = C / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = C;
+                d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = C;
+                d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C, 0, C, 0};
+                push_gemm(d);
+            }
         }
         {   // out projection + bias + residual (un-normalised input)
             ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(O, Bp, Hh, Ww, C);
@@ -1384,6 +1419,15 @@ int sr3_test_gemm(const void* a, const void* b, float* dptr, int M, int N, int K
     d.OW = M; d.OH = 1; d.OB = 1; d.n_valid = N;
     d.out_f32 = dptr; d.os = OutSpec{0, 0, 0, N, 0};
     Op op = make_gemm_op(d, mem);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    op(st);
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+int sr3_test_attention(const void* qk, const void* vT, void* out, int nz, int Lt, int HW, int C, void* stream) {
+    API_BEGIN
+    Op op = make_attn_op(static_cast<const bf16*>(qk), static_cast<const bf16*>(vT), static_cast<bf16*>(out), nz, Lt, HW, C);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     op(st);
     CK(cudaStreamSynchronize(st));

@@ -118,6 +118,9 @@ int sr3_engine_read_activation(sr3_engine* e, const char* name, float* dst, int6
 /* Stand-alone tile GEMM for unit tests: D[M,N] = A[M,K] * B[N,K]^T (bf16 row-major DEVICE inputs, fp32 output), M%128==0,
  * K%64==0, N%block_n==0. */
 int sr3_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N, int K, int block_n, void* stream);
+/* Test hook for the fused attention core (S = q k^T / sqrt(C), softmax per image, O = P v; unet.py:129-139): qk bf16 [nz*Lt][2C]
+ * (q | k), vT bf16 [nz*C][Lt], out bf16 [nz*Lt][C]; Lt in {128, 256} keys per attention batch, HW tokens per image (Lt % HW == 0). */
+int sr3_test_attention(const void* qk_bf16, const void* vT_bf16, void* out_bf16, int nz, int Lt, int HW, int C, void* stream);
 /* Stand-alone NHWC conv for unit tests: x bf16 [B,H,W,Cin], w fp32 OIHW [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
  * y fp32 [B,OH,OW,Cout]; stats (optional) fp32 [B,Cout,2] must be zeroed by the caller. */
 int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin,

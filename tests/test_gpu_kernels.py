@@ -44,3 +44,26 @@ def test_conv_matches_fp32(B, H, W, Cin, Cout, k, s):
     st = stats.cpu()
     assert torch.allclose(st[..., 0], ref.sum(dim=(2, 3)), rtol=1e-3, atol=1e-2)
     assert torch.allclose(st[..., 1], (ref * ref).sum(dim=(2, 3)), rtol=1e-3, atol=1e-2)
+
+
+@pytest.mark.parametrize("nz,Lt,HW,C", [(3, 256, 256, 512), (2, 128, 64, 512), (2, 256, 256, 128), (1, 128, 128, 256), (2, 256, 64, 256)])
+def test_fused_attention_matches_fp32(nz, Lt, HW, C):
+    """attn_kernel (S = q k^T / sqrt(C), softmax over the keys of the same image, O = P v; reference unet.py:129-139) against fp32
+    torch on the same bf16 operands.  Tolerance: P and O are rounded to bf16 (2^-9 relative each)."""
+    from sr3_b200 import _native
+    g = torch.Generator().manual_seed(nz * 1000 + Lt + HW + C)
+    q = torch.randn(nz, Lt, C, generator=g)
+    k = torch.randn(nz, Lt, C, generator=g)
+    v = torch.randn(nz, Lt, C, generator=g)
+    q = q * 2.0                                  # logits with a spread of a few units after the 1/sqrt(C) scaling
+    qk = torch.cat([q, k], dim=2).bfloat16()
+    vb = v.bfloat16()
+    vT = vb.transpose(1, 2).contiguous()         # [nz, C, Lt]
+    out = _native.test_attention(qk.reshape(nz * Lt, 2 * C).cuda(), vT.reshape(nz * C, Lt).cuda(), nz, Lt, HW, C).float().cpu().reshape(nz, Lt, C)
+    qf, kf = qk[..., :C].float(), qk[..., C:].float()
+    S = qf @ kf.transpose(1, 2) / (C ** 0.5)
+    seg = torch.arange(Lt) // HW
+    S = S.masked_fill(seg[:, None] != seg[None, :], float("-inf"))
+    ref = torch.softmax(S, dim=-1) @ vb.float()
+    assert torch.isfinite(out).all()
+    assert rel(out, ref) < 6e-3, rel(out, ref)
