@@ -127,6 +127,7 @@ struct GemmDesc {
     const float* resid = nullptr; OutSpec rs{};
     float* out_f32 = nullptr; OutSpec os{};
     bf16* out_bf16 = nullptr; OutSpec hs{};
+    bf16* out_t = nullptr; int t_col0 = 0, t_rows = 0, t_ld = 0, t_per = 1;   // transposed bf16 store of columns >= t_col0
     float* stats = nullptr; int stats_C = 0, stats_coff = 0;
     const StepCtl* ctl = nullptr; PostParams post{};
 };
@@ -288,6 +289,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.mode = d.mode; p.OW = d.OW; p.OH = d.OH; p.OB = d.OB; p.n_valid = d.n_valid; p.scale = d.scale;
     p.bias = d.bias; p.bias2 = d.bias2; p.bias2_stride = d.bias2_stride;
     p.resid = d.resid; p.rs = d.rs; p.out_f32 = d.out_f32; p.os = d.os; p.out_bf16 = d.out_bf16; p.hs = d.hs;
+    p.out_t = d.out_t; p.t_col0 = d.t_col0; p.t_rows = d.t_rows; p.t_ld = d.t_ld; p.t_per = d.t_per > 0 ? d.t_per : 1;
     p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
     if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
     // fp32 output / residual through smem + TMA: one 32-row x 32-column box per epilogue warp
@@ -810,17 +812,20 @@ struct sr3_engine {
         Act y = new_act(C, Hh, Ww, L.name);
         add_prep(x, nullptr, gn_w, gn_b, G, false, n, nullptr);
         if (dry) return y;
-        {   // q,k = Wqk n : [Bp*HW tokens] x [2C]
+        const bool merged_qkv = getenv("SR3_NO_MERGED_QKV") == nullptr && C % 128 == 0;     // whole 128-column tiles on either side of 2C
+        {   // q,k (,v) = Wqkv n : [Bp*HW tokens] x [2C (3C)]; the v columns are stored transposed as vT[z][d][token]
             GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C);
             add_conv_slabs(d.slabs, 0, C, 1, 1, 0);
-            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = 2 * C; d.b_is_param = true;
+            const int ncol = merged_qkv ? 3 * C : 2 * C;
+            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = ncol; d.b_is_param = true;
             pick_image_box(Ww, Hh, d.w_box, d.h_box, d.b_box);
-            d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = 2 * C / 128;
-            d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = 2 * C;
+            d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = ncol / 128;
+            d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = ncol;
             d.out_bf16 = qk; d.hs = nhwc_out(Hh, Ww, 2 * C);
+            if (merged_qkv) { d.out_t = vT; d.t_col0 = 2 * C; d.t_rows = C; d.t_ld = Lt; d.t_per = per; }
             push_gemm(d);
         }
-        {   // vT[z][d][token] = Wv[d,:] . n[token,:]  (weights are the A operand, tokens the B operand)
+        if (!merged_qkv) {   // vT[z][d][token] = Wv[d,:] . n[token,:]  (weights are the A operand, tokens the B operand)
             GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(wqkv + (size_t)2 * C * C, 1, C, C, C, 0);
             for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
             d.block_n = 128; d.b_ptr = n; d.b_K = C; d.b_rows = (long long)Bp * HW;

@@ -113,6 +113,10 @@ struct GemmParams {
     OutSpec os;
     __nv_bfloat16* out_bf16;
     OutSpec hs;
+    // columns >= t_col0 are stored TRANSPOSED instead: out_t[(img / t_per) * t_rows + (n - t_col0)][(img % t_per) * OH*OW + oh*OW + ow]
+    // (the v third of the qkv projection lands directly as the K-major B operand v^T of O = P v)
+    __nv_bfloat16* out_t;
+    int t_col0, t_rows, t_ld, t_per;
     float* stats;            // [B][stats_C][2] (sum, sumsq), channel offset stats_coff
     int stats_C, stats_coff;
     const StepCtl* ctl;
@@ -672,7 +676,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 if (nb + j < p.n_valid) p.out_f32[oo + nb + j] = f[j];
                         }
                     }
-                    if (row_ok && p.out_bf16) {
+                    if (p.out_t && nb >= p.t_col0) {
+                        if (ow < p.OW && oh < p.OH && nb + 32 <= p.n_valid) {          // padded images too: their (finite) values are multiplied by P = 0 later
+                            __nv_bfloat16* tp = p.out_t + (static_cast<long long>(img / p.t_per) * p.t_rows + (nb - p.t_col0)) * p.t_ld +
+                                                (img % p.t_per) * (p.OH * p.OW) + oh * p.OW + ow;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) tp[static_cast<long long>(j) * p.t_ld] = __float2bfloat16_rn(f[j]);   // lanes = consecutive tokens
+                        }
+                    } else if (row_ok && p.out_bf16) {
                         const long long ho = out_index(p.hs, z, img, oh, ow);
                         if (full) {
                             uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + ho + nb);
