@@ -627,10 +627,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     float f[32];
                     const bool full = (nb + 32 <= p.n_valid);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float x = __uint_as_float(v[j]) * ep_scale + bs[j];
-                        if (!full && nb + j >= p.n_valid) x = 0.f;
-                        f[j] = x;
+                    for (int j4 = 0; j4 < 8; ++j4) {               // bias broadcast: 8 x LDS.128 (the slot is 128 B aligned)
+                        const float4 bq = reinterpret_cast<const float4*>(bs)[j4];
+                        const float bb4[4] = {bq.x, bq.y, bq.z, bq.w};
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j = 4 * j4 + jj;
+                            float x = __uint_as_float(v[j]) * ep_scale + bb4[jj];
+                            if (!full && nb + j >= p.n_valid) x = 0.f;
+                            f[j] = x;
+                        }
                     }
                     if (use_res_tma) {
                         const uint32_t b = (res_count - 1) & 1;
