@@ -575,6 +575,9 @@ struct sr3_engine {
     int F = 0;
     cudaGraphExec_t graph = nullptr;
     cudaStream_t cap_stream = nullptr;
+    cudaStream_t side_stream = nullptr;            // graph capture only: the noise-level embedding + FiLM projections run beside the first conv
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int side_begin = -1, side_end = -1, side_join = -1;   // ops [side_begin, side_end) on the side branch, joined before op side_join
     bool use_graph = true;
     uint64_t seed = 0, first_index = 0;
     bool have_cond = false;
@@ -582,6 +585,9 @@ struct sr3_engine {
     ~sr3_engine() {
         if (graph) cudaGraphExecDestroy(graph);
         if (cap_stream) cudaStreamDestroy(cap_stream);
+        if (side_stream) cudaStreamDestroy(side_stream);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
     }
 
     // ---- buffers shared between layers of the same role (stream order makes reuse safe)
@@ -931,9 +937,11 @@ struct sr3_engine {
             EmbedParams ep{}; ep.ctl = ctl_dev; ep.nl_table = nl_table; ep.nl_buf = nl_buf; ep.w1 = mlp_w1; ep.b1 = mlp_b1; ep.w2 = mlp_w2; ep.b2 = mlp_b2;
             ep.tau = tau; ep.inner = inner;
             const int Bn = B; const int esm = 5 * inner * 4;
+            side_begin = (int)ops.size();
             push([=](cudaStream_t st) { launch_k(embed_kernel, dim3(Bn), dim3(256), (size_t)esm, st, ep); });
             float *fw = film_w, *fb = film_b, *fc = film_cb, *ta = tau, *fi = film; const int Fn = F, inn = inner;
             push([=](cudaStream_t st) { launch_k(film_kernel, dim3((Fn + 63) / 64), dim3(256), (size_t)((64 * (inn + 1) + Bn * inn) * 4), st, (const float*)fw, (const float*)fb, (const float*)fc, (const float*)ta, fi, Fn, inn, Bn); });
+            side_end = (int)ops.size();
         }
 
         int film_off = 0;
@@ -953,6 +961,7 @@ struct sr3_engine {
                 add_conv_slabs(c.slabs, 0, in_C, 3, 1, 0);
                 c.w = w; c.ktot = 9 * in_C; c.cout = inner; c.OH = H; c.OW = W; c.bias = b; c.out = x;
                 add_conv(c);
+                if (!dry) side_join = (int)ops.size();      // the FiLM biases are first read by the next block's conv1 epilogue
             } else if (L.kind == 1) {
                 bf16* xr = (fuse_cast && next_is_down) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2)) : nullptr;
                 x = add_res_block(L, x, nullptr, film_off, xr);
@@ -1109,8 +1118,24 @@ struct sr3_engine {
         if (!use_graph) { for (auto& op : ops) op(st); return; }
         if (!graph) {
             cudaGraph_t g;
+            const bool fork = getenv("SR3_NO_FORK") == nullptr && side_begin > 0 && side_end > side_begin && side_join >= side_end;
+            if (fork && !side_stream) {
+                CK(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+                CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+            }
             CK(cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-            for (auto& op : ops) op(cap_stream);
+            for (int i = 0; i < (int)ops.size(); ++i) {
+                if (fork && i == side_begin) {              // branch: embed + film depend on the step prologue only
+                    CK(cudaEventRecord(ev_fork, cap_stream));
+                    CK(cudaStreamWaitEvent(side_stream, ev_fork, 0));
+                }
+                if (fork && i == side_join) {
+                    CK(cudaEventRecord(ev_join, side_stream));
+                    CK(cudaStreamWaitEvent(cap_stream, ev_join, 0));
+                }
+                ops[i](fork && i >= side_begin && i < side_end ? side_stream : cap_stream);
+            }
             CK(cudaStreamEndCapture(cap_stream, &g));
             CK(cudaGraphInstantiate(&graph, g, 0));
             CK(cudaGraphDestroy(g));
