@@ -11,6 +11,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -145,14 +146,27 @@ int pick_stages(int block_n, int a_stage_bytes, int b_taps, bool resid, int num_
     if (s < 1) s = 1;
     return s;
 }
+int current_device() { int dev = 0; CK(cudaGetDevice(&dev)); return dev; }
 int num_sms() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        CK(cudaGetDevice(&dev));
-        CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static std::map<int, int> cache;               // per device: a process may hold engines on several GPUs
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = current_device();
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    int n = 0;
+    CK(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+    cache[dev] = n;
     return n;
+}
+// cudaFuncSetAttribute is per device: remember which devices already have the opt-in shared-memory size of a kernel family
+bool first_use_on_device(std::vector<int>& seen) {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    const int dev = current_device();
+    for (int d : seen) if (d == dev) return false;
+    seen.push_back(dev);
+    return true;
 }
 // Every kernel of the step is launched with programmatic stream serialization (PDL): its prologue overlaps the tail of the
 // previous kernel; the kernels call griddepcontrol.wait before touching upstream data.
@@ -172,8 +186,8 @@ void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
     launch_k(gemm_tile_kernel<BN, MH>, grid, dim3(GEMM_THREADS), (size_t)smem, st, p);
 }
 void init_gemm_attrs() {
-    static bool done = false;
-    if (done) return;
+    static std::vector<int> seen;
+    if (!first_use_on_device(seen)) return;
     CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -182,7 +196,6 @@ void init_gemm_attrs() {
     CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    done = true;
 }
 
 struct DevAllocs {
@@ -392,8 +405,8 @@ Op make_attn_op(const bf16* qk, const bf16* vT, bf16* out, int nz, int Lt, int H
     p.out = out; p.C = C; p.Lt = Lt; p.HW = HW;
     p.dn = (C % 256 == 0) ? 256 : 128;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)C);
-    static bool attr_done = false;
-    if (!attr_done) { CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES)); attr_done = true; }
+    static std::vector<int> seen;
+    if (first_use_on_device(seen)) CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES));
     const dim3 grid((Lt / 128) * (C / p.dn), nz, 1);
     return [p, grid](cudaStream_t st) { launch_k(attn_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM_BYTES, st, p); };
 }
