@@ -135,13 +135,14 @@ def block(sd, prefix: str, x: Tensor, groups: int, dropout_mask: Optional[Tensor
     return F.conv2d(h, sd[prefix + ".block.3.weight"], sd[prefix + ".block.3.bias"], padding=1)
 
 
-def resnet_block(sd, prefix: str, x: Tensor, t_emb: Tensor, groups: int) -> Tensor:
-    """model/sr3_modules/unet.py:94-110 (+ FeatureWiseAffine bias-only form, :34-50)."""
+def resnet_block(sd, prefix: str, x: Tensor, t_emb: Tensor, groups: int, dropout_masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """model/sr3_modules/unet.py:94-110 (+ FeatureWiseAffine bias-only form, :34-50).  Dropout exists only in block2 (:100-101);
+    `dropout_masks[prefix + ".block2"]` is the already scaled (0 or 1/(1-p)) mask of a training forward, None = eval."""
     b = x.shape[0]
     h = block(sd, prefix + ".block1", x, groups)
     film = F.linear(t_emb, sd[prefix + ".noise_func.noise_func.0.weight"], sd[prefix + ".noise_func.noise_func.0.bias"])
     h = h + film.view(b, -1, 1, 1)
-    h = block(sd, prefix + ".block2", h, groups)
+    h = block(sd, prefix + ".block2", h, groups, None if dropout_masks is None else dropout_masks.get(prefix + ".block2"))
     if (prefix + ".res_conv.weight") in sd:
         return h + F.conv2d(x, sd[prefix + ".res_conv.weight"], sd[prefix + ".res_conv.bias"])
     return h + x
@@ -160,16 +161,16 @@ def self_attention(sd, prefix: str, x: Tensor, groups: int) -> Tensor:
     return o + x
 
 
-def res_attn(sd, spec: LayerSpec, x: Tensor, t_emb: Tensor, groups: int) -> Tensor:
+def res_attn(sd, spec: LayerSpec, x: Tensor, t_emb: Tensor, groups: int, dropout_masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """model/sr3_modules/unet.py:145-158."""
-    x = resnet_block(sd, spec.name + ".res_block", x, t_emb, groups)
+    x = resnet_block(sd, spec.name + ".res_block", x, t_emb, groups, dropout_masks)
     if spec.attn:
         x = self_attention(sd, spec.name + ".attn", x, groups)
     return x
 
 
 def unet_forward(sd: Dict[str, Tensor], cfg: UNetConfig, x: Tensor, noise_level: Tensor,
-                 taps: Optional[Dict[str, Tensor]] = None) -> Tensor:
+                 taps: Optional[Dict[str, Tensor]] = None, dropout_masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
     """model/sr3_modules/unet.py:235-259.  x [B,Cin,H,W], noise_level [B,1] -> eps [B,Cout,H,W].
 
     `sd` keys are relative to the UNet (no 'denoise_fn.' prefix).  If `taps` is a dict,
@@ -184,12 +185,12 @@ def unet_forward(sd: Dict[str, Tensor], cfg: UNetConfig, x: Tensor, noise_level:
         elif spec.kind == "down":
             x = F.conv2d(x, sd[spec.name + ".conv.weight"], sd[spec.name + ".conv.bias"], stride=2, padding=1)
         else:
-            x = res_attn(sd, spec, x, t, g)
+            x = res_attn(sd, spec, x, t, g, dropout_masks)
         feats.append(x)
         if taps is not None:
             taps[spec.name] = x
     for spec in mid:
-        x = res_attn(sd, spec, x, t, g)
+        x = res_attn(sd, spec, x, t, g, dropout_masks)
         if taps is not None:
             taps[spec.name] = x
     for spec in ups:
@@ -197,7 +198,7 @@ def unet_forward(sd: Dict[str, Tensor], cfg: UNetConfig, x: Tensor, noise_level:
             x = F.interpolate(x, scale_factor=2, mode="nearest")
             x = F.conv2d(x, sd[spec.name + ".conv.weight"], sd[spec.name + ".conv.bias"], padding=1)
         else:
-            x = res_attn(sd, spec, torch.cat((x, feats.pop()), dim=1), t, g)
+            x = res_attn(sd, spec, torch.cat((x, feats.pop()), dim=1), t, g, dropout_masks)
         if taps is not None:
             taps[spec.name] = x
     return block(sd, "final_conv", x, g)
@@ -321,15 +322,41 @@ def q_sample(x_start: Tensor, gamma: Tensor, noise: Tensor) -> Tensor:
     return gamma * x_start + (1 - gamma ** 2).sqrt() * noise
 
 
-def p_losses(sd, cfg, sch, hr: Tensor, sr: Optional[Tensor], gamma: Tensor, noise: Tensor, loss_type: str = "l1") -> Tensor:
-    """model/sr3_modules/diffusion.py:221-246 with t / gamma / noise injected (gamma [B])."""
+def p_losses(sd, cfg, sch, hr: Tensor, sr: Optional[Tensor], gamma: Tensor, noise: Tensor, loss_type: str = "l1",
+             dropout_masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """model/sr3_modules/diffusion.py:221-246 with t / gamma / noise injected (gamma [B]); `dropout_masks` = the masks of a
+    training-mode forward (see resnet_block), None = eval-mode network."""
     b = hr.shape[0]
     x_noisy = q_sample(hr, gamma.view(-1, 1, 1, 1), noise)
     inp = torch.cat([sr, x_noisy], dim=1) if sr is not None else x_noisy
-    recon = unet_forward(sd, cfg, inp, gamma.view(b, -1))
+    recon = unet_forward(sd, cfg, inp, gamma.view(b, -1), None, dropout_masks)
     if loss_type == "l1":
         return (noise - recon).abs().sum()
     return ((noise - recon) ** 2).sum()
+
+
+def train_loss(sd, cfg, sch, hr: Tensor, sr: Optional[Tensor], gamma: Tensor, noise: Tensor, loss_type: str = "l1",
+               dropout_masks: Optional[Dict[str, Tensor]] = None) -> Tensor:
+    """The scalar DDPM.optimize_parameters back-propagates: l_pix.sum() / int(b*c*h*w)  (model/model.py:48-53)."""
+    b, c, h, w = hr.shape
+    return p_losses(sd, cfg, sch, hr, sr, gamma, noise, loss_type, dropout_masks) / int(b * c * h * w)
+
+
+def make_adam(sd: Dict[str, Tensor], lr: float = 1e-4):
+    """The optimizer of model/model.py:39-40: torch.optim.Adam(params, lr) with torch defaults (betas (0.9, 0.999), eps 1e-8,
+    weight_decay 0), over the parameters in state_dict order.  Marks the tensors of `sd` as leaves that require grad."""
+    for v in sd.values():
+        v.requires_grad_(True)
+    return torch.optim.Adam(list(sd.values()), lr=lr)
+
+
+def train_step(sd, opt, cfg, sch, hr, sr, gamma, noise, loss_type: str = "l1", dropout_masks=None) -> float:
+    """One DDPM.optimize_parameters iteration (model/model.py:48-58) with the random draws injected; returns l_pix."""
+    opt.zero_grad()
+    loss = train_loss(sd, cfg, sch, hr, sr, gamma, noise, loss_type, dropout_masks)
+    loss.backward()
+    opt.step()
+    return float(loss.item())
 
 
 def draw_gamma(sch: Schedule, batch: int, rng: np.random.RandomState):
