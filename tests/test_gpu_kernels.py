@@ -84,3 +84,24 @@ def test_split_k_conv_is_deterministic(B, H, W, Cin, Cout):
     assert torch.equal(y1, y2)
     ref = F.conv2d(x.float(), w.bfloat16().float(), bias, stride=1, padding=1)
     assert rel(y1.cpu().permute(0, 3, 1, 2), ref) < 2e-5
+
+
+def dgrad_weights(w):
+    """Weights W' such that conv3x3(dY, W', pad 1) = dL/dX of y = conv3x3(X, W, pad 1): W'[ci, co, r, s] = W[co, ci, 2-r, 2-s]."""
+    return w.flip(2, 3).transpose(0, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 16, 16, 64, 128), (1, 32, 32, 128, 64), (2, 8, 8, 512, 512)])
+def test_conv_dgrad_is_the_forward_kernel_on_mirrored_weights(B, H, W, Cin, Cout):
+    """Training row, data gradient of a stride-1 conv3x3: the same implicit-GEMM tile kernel run on dY with mirrored taps and
+    Cin <-> Cout swapped, against torch autograd (fp32 on the same bf16-rounded operands)."""
+    from sr3_b200 import _native
+    g = torch.Generator().manual_seed(B * 3 + H + Cin * 7 + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g, requires_grad=True)
+    w = (torch.randn(Cout, Cin, 3, 3, generator=g) * (1.0 / (Cin * 9) ** 0.5)).bfloat16().float()
+    dy = torch.randn(B, Cout, H, W, generator=g).bfloat16()
+    y = F.conv2d(x, w, None, padding=1)
+    (dx_ref,) = torch.autograd.grad(y, x, dy.float())
+    zero_bias = torch.zeros(Cin)
+    dx, _ = _native.test_conv(dy.permute(0, 2, 3, 1).contiguous().cuda(), dgrad_weights(w).cuda(), zero_bias.cuda(), 3, 1, want_stats=True)
+    assert rel(dx.cpu().permute(0, 3, 1, 2), dx_ref) < 2e-5

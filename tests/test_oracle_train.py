@@ -91,3 +91,16 @@ def test_training_mode_dropout_forward_backward(train_golden):
     with torch.no_grad():
         ev = orc.train_loss(sd, cfg, sch, hr, sr, gamma, noise)
     assert abs(ev.item() - d["loss"]) > 1e-5
+
+
+def test_dgrad_identity_used_by_the_gpu_test():
+    """conv3x3(dY, W') with W'[ci, co, r, s] = W[co, ci, 2-r, 2-s] is the data gradient of conv3x3(X, W) (stride 1, pad 1): the
+    identity behind tests/test_gpu_kernels.py::test_conv_dgrad_is_the_forward_kernel_on_mirrored_weights, checked on CPU."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 6, 9, 7, generator=g, requires_grad=True)
+    w = torch.randn(5, 6, 3, 3, generator=g)
+    dy = torch.randn(2, 5, 9, 7, generator=g)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, None, padding=1), x, dy)
+    wp = w.flip(2, 3).transpose(0, 1).contiguous()
+    assert torch.allclose(F.conv2d(dy, wp, None, padding=1), ref, atol=1e-5, rtol=1e-5)
