@@ -5,6 +5,8 @@ reference's Python interface.  There is no CPU / eager fallback: without the lib
 from . import _native  # noqa: F401
 from .model import networks  # noqa: F401
 from .model.networks import define_G  # noqa: F401
+from .model.sr3_modules.diffusion import GaussianDiffusion  # noqa: F401
+from .model.sr3_modules.unet import UNet  # noqa: F401
 
-__all__ = ["define_G", "networks"]
+__all__ = ["define_G", "networks", "GaussianDiffusion", "UNet"]
 __version__ = "0.1.0"

@@ -1,0 +1,76 @@
+"""Drop-in check at the boundary SURVEY.md 8b names: the UNMODIFIED reference wrapper (model/model.py `DDPM`, created through
+`model.create_model(opt)`) is run with `model.networks.define_G` replaced by `sr3_b200.define_G` -- the one-line change INTEGRATION.md
+describes.  Everything the wrapper does with netG short of GPU compute is exercised here on CPU: construction, set_device, set_loss,
+set_new_noise_schedule (both phases), print_network, the Adam optimizer over our parameters, save_network / load_network with the
+reference's file naming and strict key matching, and a checkpoint written by the reference's own netG.
+
+Needs the reference checkout (build container only; the GPU box has no /root/reference -> skipped there)."""
+import os
+import sys
+
+import pytest
+import torch
+
+REF = os.environ.get("SR3_REFERENCE", "/root/reference")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model")), reason="reference checkout not present")
+
+SCHED = {"schedule": "linear", "n_timestep": 20, "linear_start": 1e-6, "linear_end": 1e-2}
+TINY = dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2], attn_res=[16], res_blocks=1, dropout=0.0)
+
+
+def make_opt(phase, ckpt_dir, resume=None):
+    return {"phase": phase, "gpu_ids": None, "distributed": False,
+            "path": {"checkpoint": ckpt_dir, "resume_state": resume},
+            "train": {"optimizer": {"type": "adam", "lr": 1e-4}},
+            "model": {"which_model_G": "sr3", "finetune_norm": False, "unet": dict(TINY),
+                      "beta_schedule": {"train": dict(SCHED), "val": dict(SCHED)},
+                      "diffusion": {"image_size": 32, "channels": 3, "conditional": True}}}
+
+
+@pytest.fixture()
+def ref_model_pkg(monkeypatch):
+    """The reference's `model` package with define_G swapped for ours (and restored afterwards)."""
+    sys.dont_write_bytecode = True
+    monkeypatch.syspath_prepend(REF)
+    for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        monkeypatch.delitem(sys.modules, k)
+    import model as ref_model                      # /root/reference/model/__init__.py
+    import model.networks as ref_networks
+    import sr3_b200
+    orig = ref_networks.define_G
+    monkeypatch.setattr(ref_networks, "define_G", sr3_b200.define_G)
+    yield ref_model, ref_networks, orig
+    for k in [k for k in sys.modules if k == "model" or k.startswith("model.")]:
+        sys.modules.pop(k, None)
+
+
+def test_reference_ddpm_wrapper_runs_on_our_define_g(ref_model_pkg, tmp_path):
+    ref_model, ref_networks, orig_define_G = ref_model_pkg
+    import sr3_b200
+    torch.manual_seed(0)
+    m = ref_model.create_model(make_opt("train", str(tmp_path)))
+    assert type(m.netG).__name__ == "GaussianDiffusion" and isinstance(m.netG, sr3_b200.GaussianDiffusion)
+    s, n = m.get_network_description(m.netG)
+    assert n == sum(p.numel() for p in m.netG.parameters()) and "GaussianDiffusion" in s
+    assert len(m.optG.param_groups[0]["params"]) == len(list(m.netG.parameters()))
+    # phase switch as sr.py does (sr.py:110-111,146-147)
+    m.set_new_noise_schedule(make_opt("val", "")["model"]["beta_schedule"]["val"], schedule_phase="val")
+    assert m.netG.num_timesteps == SCHED["n_timestep"] and m.netG.betas.device.type == "cpu"
+    # checkpoint round trip with the reference's naming (model.py:124-166)
+    m.save_network(epoch=3, iter_step=70)
+    gen, optp = tmp_path / "I70_E3_gen.pth", tmp_path / "I70_E3_opt.pth"
+    assert gen.exists() and optp.exists()
+    torch.manual_seed(1)                                          # different init, then resume
+    m2 = ref_model.create_model(make_opt("train", str(tmp_path), resume=str(tmp_path / "I70_E3")))
+    assert m2.begin_step == 70 and m2.begin_epoch == 3
+    for (k1, v1), (k2, v2) in zip(m.netG.state_dict().items(), m2.netG.state_dict().items()):
+        assert k1 == k2 and torch.equal(v1, v2), k1
+    # a checkpoint written by the reference's OWN network loads strictly into ours, and the other way round
+    torch.manual_seed(2)
+    ref_net = orig_define_G(make_opt("val", ""))
+    ref_net.set_new_noise_schedule(SCHED, "cpu")                  # as DDPM.__init__ does before any save (model.py:21-22)
+    torch.save(ref_net.state_dict(), tmp_path / "I1_E1_gen.pth")
+    m3 = ref_model.create_model(make_opt("val", str(tmp_path), resume=str(tmp_path / "I1_E1")))
+    for k, v in ref_net.state_dict().items():
+        assert torch.equal(m3.netG.state_dict()[k], v), k
+    ref_net.load_state_dict(m.netG.state_dict(), strict=True)
