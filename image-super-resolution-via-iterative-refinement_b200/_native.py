@@ -50,6 +50,7 @@ _SIGS = {
     "sr3_bench_conv": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "sr3_test_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sr3_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "sr3_test_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "sr3_test_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
 }
@@ -285,6 +286,15 @@ def test_attention(qk_bf16, vT_bf16, nz, Lt, HW, C):
     out = torch.empty(nz * Lt, C, device=qk_bf16.device, dtype=torch.bfloat16)
     _check(lib().sr3_test_attention(_ptr(qk_bf16), _ptr(vT_bf16), _ptr(out), nz, Lt, HW, C, _stream()))
     return out
+
+
+def test_wgrad(dy_nhwc_bf16, x_nhwc_bf16):
+    """EXPERIMENTAL: conv3x3 (stride 1, pad 1) weight gradient -> fp32 [Cout, 9, Cin]."""
+    B, H, W, Cout = dy_nhwc_bf16.shape
+    Cin = x_nhwc_bf16.shape[3]
+    dw = torch.empty(Cout, 9, Cin, device=x_nhwc_bf16.device, dtype=torch.float32)
+    _check(lib().sr3_test_wgrad(_ptr(dy_nhwc_bf16), _ptr(x_nhwc_bf16), _ptr(dw), B, H, W, Cin, Cout, _stream()))
+    return dw
 
 
 def test_gemm(a_bf16, b_bf16, block_n):

@@ -19,6 +19,7 @@
 #include "../../include/sr3_b200.h"
 #include "aux_kernels.cuh"
 #include "attn_tcgen05.cuh"
+#include "wgrad_tcgen05.cuh"
 
 using namespace sr3;
 typedef __nv_bfloat16 bf16;
@@ -1473,6 +1474,36 @@ int sr3_test_attention(const void* qk, const void* vT, void* out, int nz, int Lt
     Op op = make_attn_op(static_cast<const bf16*>(qk), static_cast<const bf16*>(vT), static_cast<bf16*>(out), nz, Lt, HW, C);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     op(st);
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+// EXPERIMENTAL (training row): weight gradient of a stride-1 conv3x3 with MN-major tcgen05 operands (wgrad_tcgen05.cuh).
+int sr3_test_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, void* stream) {
+    API_BEGIN
+    REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && H % 8 == 0 && W % 8 == 0 && B >= 1, "bad test wgrad shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    WgradParams p;
+    memset(&p, 0, sizeof(p));
+    auto mk = [&](const void* ptr, int C) {
+        const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1ull, (uint64_t)H, (uint64_t)B};
+        const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+        const uint32_t box[5] = {64u, 8u, 1u, 8u, 1u};
+        return encode_map(5, ptr, dims, str, box);
+    };
+    p.dy_map = mk(dy, Cout); p.x_map = mk(x, Cin);
+    p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.B = B;
+    const int tiles_mn = ((Cout + 127) / 128) * (Cin / 64) * 3;
+    int slices = num_sms() / tiles_mn;                         // batch slices so that about one wave of CTAs runs
+    if (slices < 1) slices = 1;
+    if (slices > B) slices = B;
+    p.b_per_cta = (B + slices - 1) / slices;
+    slices = (B + p.b_per_cta - 1) / p.b_per_cta;
+    static std::vector<int> seen;
+    if (first_use_on_device(seen)) CK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
+    CK(cudaMemsetAsync(dw, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
+    wgrad_kernel<<<dim3(((Cout + 127) / 128) * (Cin / 64), 3, slices), dim3(WGRAD_THREADS), WGRAD_SMEM_BYTES, st>>>(p);
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(st));
     API_END
 }

@@ -123,6 +123,10 @@ int sr3_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N
 /* Test hook for the fused attention core (S = q k^T / sqrt(C), softmax per image, O = P v; unet.py:129-139): qk bf16 [nz*Lt][2C]
  * (q | k), vT bf16 [nz*C][Lt], out bf16 [nz*Lt][C]; Lt in {128, 256} keys per attention batch, HW tokens per image (Lt % HW == 0). */
 int sr3_test_attention(const void* qk_bf16, const void* vT_bf16, void* out_bf16, int nz, int Lt, int HW, int C, void* stream);
+/* EXPERIMENTAL test hook for the training row (not used by any product path): weight gradient of a stride-1 conv3x3,
+ * dW[co][tap][ci] = sum_pixels dY[p][co] * X[p+tap][ci]  (the wgrad of nn.Conv2d in unet.py:87, model.py:53 backward);
+ * dy bf16 NHWC [B,H,W,Cout], x bf16 NHWC [B,H,W,Cin], dw fp32 [Cout][9][Cin] (overwritten). */
+int sr3_test_wgrad(const void* dy_bf16, const void* x_bf16, float* dw, int B, int H, int W, int Cin, int Cout, void* stream);
 /* Stand-alone NHWC conv for unit tests: x bf16 [B,H,W,Cin], w fp32 OIHW [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
  * y fp32 [B,OH,OW,Cout]; stats (optional) fp32 [B,Cout,2] must be zeroed by the caller. */
 int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin,

@@ -105,3 +105,19 @@ def test_conv_dgrad_is_the_forward_kernel_on_mirrored_weights(B, H, W, Cin, Cout
     zero_bias = torch.zeros(Cin)
     dx, _ = _native.test_conv(dy.permute(0, 2, 3, 1).contiguous().cuda(), dgrad_weights(w).cuda(), zero_bias.cuda(), 3, 1, want_stats=True)
     assert rel(dx.cpu().permute(0, 3, 1, 2), dx_ref) < 2e-5
+
+
+@pytest.mark.skipif(__import__("os").environ.get("SR3_EXPERIMENTAL") != "1",
+                    reason="experimental training-row kernel (wgrad_tcgen05.cuh) not yet validated on a B200: set SR3_EXPERIMENTAL=1")
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(1, 8, 8, 64, 64), (2, 16, 16, 64, 128), (3, 32, 32, 128, 64)])
+def test_experimental_wgrad_matches_autograd(B, H, W, Cin, Cout):
+    """dW of a stride-1 conv3x3 with MN-major tcgen05 operands against torch autograd on the same bf16 operands."""
+    from sr3_b200 import _native
+    g = torch.Generator().manual_seed(B + H + Cin + Cout)
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16()
+    dy = torch.randn(B, Cout, H, W, generator=g).bfloat16()
+    w = torch.zeros(Cout, Cin, 3, 3, requires_grad=True)
+    (dw_ref,) = torch.autograd.grad(F.conv2d(x.float(), w, None, padding=1), w, dy.float())
+    dw = _native.test_wgrad(dy.permute(0, 2, 3, 1).contiguous().cuda(), x.permute(0, 2, 3, 1).contiguous().cuda()).cpu()
+    ref = dw_ref.permute(0, 2, 3, 1).reshape(Cout, 9, Cin)          # [co][r*3+s][ci]
+    assert rel(dw, ref) < 1e-4, rel(dw, ref)
