@@ -45,12 +45,16 @@ _SIGS = {
     "sr3_engine_profile_step": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_float), POINTER(c_double), POINTER(c_double),
                                         POINTER(c_int), c_void_p]),
     "sr3_engine_num_launches_per_step": (c_int, [c_void_p]),
+    "sr3_engine_num_ops_per_step": (c_int, [c_void_p]),
+    "sr3_engine_uses_step_kernel": (c_int, [c_void_p]),
+    "sr3_engine_step_kernel_profile": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_double), POINTER(c_int), c_void_p]),
     "sr3_engine_workspace_bytes": (c_int64, [c_void_p]),
     "sr3_engine_read_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int), c_void_p]),
     "sr3_bench_conv": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
     "sr3_test_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "sr3_test_attention": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
-    "sr3_test_wgrad": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "sr3_test_conv_groupnorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                        c_int, c_void_p]),
     "sr3_test_conv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                               c_void_p]),
 }
@@ -251,7 +255,7 @@ class Engine:
 
     def profile_step(self, t, reps=3):
         """[(kind, ms, flops, bytes)] per launch of one eager step (kinds: 0 gemm tile, 1 GN apply, 2 cast, 3 softmax, 4 other)."""
-        cap = self.launches_per_step()
+        cap = lib().sr3_engine_num_ops_per_step(self._h)
         kinds, ms = (c_int * cap)(), (c_float * cap)()
         fl, by = (c_double * cap)(), (c_double * cap)()
         n = c_int()
@@ -261,6 +265,23 @@ class Engine:
 
     def launches_per_step(self):
         return lib().sr3_engine_num_launches_per_step(self._h)
+
+    def ops_per_step(self):
+        return lib().sr3_engine_num_ops_per_step(self._h)
+
+    def uses_step_kernel(self):
+        return bool(lib().sr3_engine_uses_step_kernel(self._h))
+
+    STEP_OP_NAMES = {0: "gemm_tile", 1: "groupnorm_apply", 2: "attention", 3: "softmax", 4: "embed_film", 5: "stats_clear"}
+
+    def step_kernel_profile(self):
+        """[(op type, microseconds)] of the most recent persistent-step-kernel launch (device globaltimer stamps)."""
+        cap = 4096
+        types, us = (c_int * cap)(), (c_double * cap)()
+        n = c_int()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_engine_step_kernel_profile(self._h, cap, types, us, ctypes.byref(n), _stream()))
+        return [(types[i], us[i]) for i in range(n.value)]
 
     def workspace_bytes(self):
         return lib().sr3_engine_workspace_bytes(self._h)
@@ -288,15 +309,6 @@ def test_attention(qk_bf16, vT_bf16, nz, Lt, HW, C):
     return out
 
 
-def test_wgrad(dy_nhwc_bf16, x_nhwc_bf16):
-    """EXPERIMENTAL: conv3x3 (stride 1, pad 1) weight gradient -> fp32 [Cout, 9, Cin]."""
-    B, H, W, Cout = dy_nhwc_bf16.shape
-    Cin = x_nhwc_bf16.shape[3]
-    dw = torch.empty(Cout, 9, Cin, device=x_nhwc_bf16.device, dtype=torch.float32)
-    _check(lib().sr3_test_wgrad(_ptr(dy_nhwc_bf16), _ptr(x_nhwc_bf16), _ptr(dw), B, H, W, Cin, Cout, _stream()))
-    return dw
-
-
 def test_gemm(a_bf16, b_bf16, block_n):
     M, K = a_bf16.shape
     N = b_bf16.shape[0]
@@ -309,6 +321,17 @@ def test_conv(x_nhwc_bf16, w_oihw, bias, ksize, stride, want_stats=False):
     B, H, W, Cin = x_nhwc_bf16.shape
     Cout = w_oihw.shape[0]
     y = torch.empty(B, H // stride, W // stride, Cout, device=x_nhwc_bf16.device, dtype=torch.float32)
-    stats = torch.zeros(B, Cout, 2, device=y.device, dtype=torch.float32) if want_stats else None
+    stats = torch.zeros(B, Cout, 2, device=y.device, dtype=torch.float64) if want_stats else None
     _check(lib().sr3_test_conv(_ptr(x_nhwc_bf16), _ptr(w_oihw), _ptr(bias), _ptr(y), _ptr(stats), B, H, W, Cin, Cout, ksize, stride, _stream()))
     return y, stats
+
+
+def test_conv_groupnorm(x_nhwc_bf16, w_oihw, bias, gamma, beta, groups, silu, ksize):
+    """conv (+ statistics in the epilogue) -> GroupNorm(+SiLU) apply: returns (y fp32 NHWC, a bf16 NHWC)."""
+    B, H, W, Cin = x_nhwc_bf16.shape
+    Cout = w_oihw.shape[0]
+    y = torch.empty(B, H, W, Cout, device=x_nhwc_bf16.device, dtype=torch.float32)
+    a = torch.empty(B, H, W, Cout, device=x_nhwc_bf16.device, dtype=torch.bfloat16)
+    _check(lib().sr3_test_conv_groupnorm(_ptr(x_nhwc_bf16), _ptr(w_oihw), _ptr(bias), _ptr(gamma), _ptr(beta), groups, int(silu), _ptr(y), _ptr(a),
+                                         B, H, W, Cin, Cout, ksize, _stream()))
+    return y, a

@@ -8,15 +8,20 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libsr3_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["ptx.cuh", "gemm_tcgen05.cuh", "aux_kernels.cuh", os.path.join("..", "..", "include", "sr3_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-Xptxas", "-v", "-shared", "-cudart", "static"]
 
 
 def _digest():
+    """sha256 over EVERY file under csrc/ (recursively) and the public header: editing any kernel source triggers a rebuild."""
     h = hashlib.sha256()
-    for f in SOURCES + HEADERS:
-        with open(os.path.join(CSRC, f), "rb") as fh:
+    files = []
+    for d, _dirs, names in os.walk(CSRC):
+        files += [os.path.join(d, n) for n in names if n.endswith((".cu", ".cuh", ".h"))]
+    files.append(os.path.join(PKG, "..", "include", "sr3_b200.h"))
+    for f in sorted(files):
+        h.update(os.path.relpath(f, PKG).encode())
+        with open(f, "rb") as fh:
             h.update(fh.read())
     h.update(" ".join(NVCC_FLAGS).encode())
     return h.hexdigest()

@@ -14,7 +14,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda.h>
-#include "ptx.cuh"
+#include "gemm_tcgen05.cuh"
 
 namespace sr3 {
 
@@ -22,58 +22,66 @@ constexpr int ATTN_THREADS = 192;
 constexpr int ATTN_STAGES = 3;
 constexpr int ATTN_STAGE_BYTES = 16384 + 32768;          // A: 128 rows x 64 | B: up to 256 rows x 64 (bf16, 128B-swizzled)
 constexpr int ATTN_P_BYTES = 65536;                      // P: 128 rows x up to 256 keys, as K chunks of 64
-constexpr int ATTN_SMEM_BYTES = 1024 + ATTN_STAGES * ATTN_STAGE_BYTES + ATTN_P_BYTES + 256;
+constexpr int ATTN_SMEM_BYTES = 1024 + GEMM_HDR_BYTES + ATTN_STAGES * ATTN_STAGE_BYTES + ATTN_P_BYTES;   // header: barriers + TMEM slot
 constexpr uint32_t ATTN_O_COL = 256;                     // TMEM: S in columns [0, Lt), O in [256, 256 + DN)
 
 struct AttnParams {
     CUtensorMap qk_map;      // 2-D bf16 [nz*Lt rows][2C], box {64, 128}
     CUtensorMap vt_map;      // 2-D bf16 [nz*C rows][Lt], box {64, 128}
     __nv_bfloat16* out;      // [nz*Lt][C]
-    int C, Lt, HW, dn;
+    int C, Lt, HW, dn, nz;
     float scale_log2e;       // log2(e) / sqrt(C)
 };
 
-__global__ void __launch_bounds__(ATTN_THREADS, 1) attn_kernel(const __grid_constant__ AttnParams p) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* base_ptr = smem_raw + (base - raw);
+// One (attention batch z, query tile qt, channel slice dc) unit.  MEGA = false: the body of attn_kernel (one unit per CTA, the kernel owns
+// barriers and TMEM).  MEGA = true: called by step_kernel for every unit of this CTA; `pm` is the global-memory copy of the parameters
+// (TMA descriptors), TMEM was allocated by the caller; warps >= 6 only take part in the block-wide barriers.
+template <bool MEGA>
+__device__ __forceinline__ void attn_unit(const AttnParams& p, const AttnParams* pm, const uint32_t base_in, uint8_t* base_ptr_in,
+                                          const uint32_t tmem_base_in, const int qt, const int dc, const int z) {
+    const uint32_t bar_base = base_in;                                 // header (gemm_tcgen05.cuh)
+    const uint32_t base = base_in + GEMM_HDR_BYTES;
+    uint8_t* base_ptr = base_ptr_in + GEMM_HDR_BYTES;
     const uint32_t p_base = base + ATTN_STAGES * ATTN_STAGE_BYTES;
     uint8_t* p_ptr = base_ptr + ATTN_STAGES * ATTN_STAGE_BYTES;
-    const uint32_t bar_base = p_base + ATTN_P_BYTES;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (ATTN_STAGES + s); };
     const uint32_t s_full = bar_base + 8u * (2 * ATTN_STAGES);
     const uint32_t p_ready = s_full + 8u;
     const uint32_t o_full = s_full + 16u;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(p_ptr + ATTN_P_BYTES + 8 * (2 * ATTN_STAGES + 3));
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr_in + HDR_TMEM_SLOT);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int n_dc = p.C / p.dn;
-    const int qt = blockIdx.x / n_dc, dc = blockIdx.x % n_dc, z = blockIdx.y;
     const int kc1 = p.C / 64;        // K chunks of S = q k^T
     const int kc3 = p.Lt / 64;       // K chunks of O = P v
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.qk_map);
-        tma_prefetch_desc(&p.vt_map);
+        tma_prefetch_desc(&pm->qk_map);
+        tma_prefetch_desc(&pm->vt_map);
+        if constexpr (MEGA) {
+            for (int i = 0; i < HDR_NUM_BARS; ++i) mbar_inval(bar_base + 8u * i);
+        }
         for (int s = 0; s < ATTN_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         mbar_init(s_full, 1);
         mbar_init(p_ready, 4);       // one arrive per softmax warp
         mbar_init(o_full, 1);
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
-        tmem_relinquish();
+    if constexpr (!MEGA) {
+        if (warp == 1) {
+            tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    pdl_launch_dependents();
-    pdl_wait();                      // q, k, vT come from the two preceding launches
+    const uint32_t tmem_base = MEGA ? tmem_base_in : *tmem_slot;
+    if constexpr (!MEGA) {
+        pdl_launch_dependents();
+        pdl_wait();                  // q, k, vT come from the two preceding launches
+    }
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -85,17 +93,24 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_kernel(const __grid_cons
                 const uint32_t dst = base + s * ATTN_STAGE_BYTES;
                 if (it < kc1) {
                     mbar_arrive_expect_tx(full_bar(s), 16384 + p.Lt * 128);
-                    tma_load_2d(dst, &p.qk_map, full_bar(s), it * 64, z * p.Lt + qt * 128);
+                    tma_load_2d(dst, &pm->qk_map, full_bar(s), it * 64, z * p.Lt + qt * 128);
                     for (int j = 0; j < p.Lt / 128; ++j)
-                        tma_load_2d(dst + 16384 + j * 16384, &p.qk_map, full_bar(s), p.C + it * 64, z * p.Lt + j * 128);
+                        tma_load_2d(dst + 16384 + j * 16384, &pm->qk_map, full_bar(s), p.C + it * 64, z * p.Lt + j * 128);
                 } else {
                     mbar_arrive_expect_tx(full_bar(s), p.dn * 128);
                     for (int j = 0; j < p.dn / 128; ++j)
-                        tma_load_2d(dst + 16384 + j * 16384, &p.vt_map, full_bar(s), (it - kc1) * 64, z * p.C + dc * p.dn + j * 128);
+                        tma_load_2d(dst + 16384 + j * 16384, &pm->vt_map, full_bar(s), (it - kc1) * 64, z * p.C + dc * p.dn + j * 128);
                 }
             }
             __syncwarp();
             if (++s == ATTN_STAGES) { s = 0; ph ^= 1u; }
+        }
+        if constexpr (MEGA) {        // tail: no commit arrival may be in flight when the barriers are recycled
+            const int total = kc1 + kc3, n_wait = total < ATTN_STAGES ? total : ATTN_STAGES;
+            for (int i = 0; i < n_wait; ++i) {
+                mbar_wait(empty_bar(s), ph ^ 1u, 16);
+                if (++s == ATTN_STAGES) { s = 0; ph ^= 1u; }
+            }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
@@ -132,7 +147,7 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_kernel(const __grid_cons
             __syncwarp();
             if (++s == ATTN_STAGES) { s = 0; ph ^= 1u; }
         }
-    } else {
+    } else if (warp < 6) {
         // ------------------------------------------------------------ softmax + epilogue: thread = one query row
         const int q = warp & 3;                            // TMEM lane quadrant this warp may access
         const int row = q * 32 + lane;
@@ -216,9 +231,23 @@ __global__ void __launch_bounds__(ATTN_THREADS, 1) attn_kernel(const __grid_cons
             }
         }
     }
+    if constexpr (MEGA) {
+        __threadfence();
+        fence_proxy_async_all();
+    }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, 512);
+    if constexpr (!MEGA) {
+        if (warp == 1) tmem_dealloc(tmem_base, 512);
+    }
+}
+
+__global__ void __launch_bounds__(ATTN_THREADS, 1) attn_kernel(const __grid_constant__ AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const int n_dc = p.C / p.dn;
+    attn_unit<false>(p, &p, base, smem_raw + (base - raw), 0u, blockIdx.x / n_dc, blockIdx.x % n_dc, blockIdx.y);
 }
 
 }  // namespace sr3

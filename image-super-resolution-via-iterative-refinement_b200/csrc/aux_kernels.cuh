@@ -22,14 +22,44 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
 // reference: nn.GroupNorm(groups, C, eps=1e-5) + Swish of Block (unet.py:80-91), torch.cat of unet.py:255.
 struct PrepParams {
     const float* src0; const float* src1;
-    const float* st0; const float* st1;     // [B][C0][2], [B][C1][2]
+    const double* st0; const double* st1;   // [B][C0][2], [B][C1][2]: fp64 (sum, sumsq) of the producing epilogues
     int C0, C1;
     const float* gamma; const float* beta;
     int groups, HW, pix_per_block, silu;
     float eps;
     __nv_bfloat16* out_a;                   // [B][HW][C0+C1]
     __nv_bfloat16* out_raw;                 // optional bf16(x), same shape
+    int B, items_per_image;                 // persistent step kernel: work items = B x items_per_image blocks of pix_per_block pixels
 };
+
+// Per-(image, channel) scale / shift of a GroupNorm from the fp64 channel sums: y = x * sc[c] + sh[c].
+// sc / sh: [C] floats in shared memory; scratch gm / gr: [groups] each.  Ends with a __syncthreads().
+__device__ __forceinline__ void groupnorm_scale_shift(const PrepParams& p, int b, float* sc, float* sh, float* gm, float* gr) {
+    const int C = p.C0 + p.C1;
+    const int gs = C / p.groups;
+    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+        double s = 0.0, q = 0.0;
+        for (int j = 0; j < gs; ++j) {
+            const int c = g * gs + j;
+            const double2 st = (c < p.C0) ? __ldcg(reinterpret_cast<const double2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
+                                          : __ldcg(reinterpret_cast<const double2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
+            s += st.x; q += st.y;
+        }
+        const double inv = 1.0 / (static_cast<double>(gs) * static_cast<double>(p.HW));
+        const double mean = s * inv;
+        double var = q * inv - mean * mean;                 // fp64: no cancellation problem for |mean| >> std
+        if (var < 0.0) var = 0.0;
+        gm[g] = static_cast<float>(mean);
+        gr[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const int g = c / gs;
+        const float k = gr[g] * __ldg(&p.gamma[c]);
+        sc[c] = k; sh[c] = __ldg(&p.beta[c]) - gm[g] * k;
+    }
+    __syncthreads();
+}
 
 // Block size = (C/4) * k threads: every thread owns ONE 4-channel column for the whole kernel (scale / shift live in
 // registers, no shared-memory or integer-division traffic in the streaming loop) and walks pixels k at a time.
@@ -38,38 +68,19 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
     pdl_wait();
     extern __shared__ float sm[];
     const int C = p.C0 + p.C1;
-    float* sc = sm;              // [C] scale   (first used as per-channel sum)
-    float* sh = sm + C;          // [C] shift   (first used as per-channel sum of squares)
+    float* sc = sm;              // [C] scale
+    float* sh = sm + C;          // [C] shift
     float* gm = sm + 2 * C;      // [groups] mean
     float* gr = gm + p.groups;   // [groups] rstd
     const int b = blockIdx.y;
-    const int gs = C / p.groups;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float2 st = (c < p.C0) ? __ldg(reinterpret_cast<const float2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
-                                     : __ldg(reinterpret_cast<const float2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
-        sc[c] = st.x; sh[c] = st.y;
-    }
-    __syncthreads();
-    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
-        float s = 0.f, q = 0.f;
-        for (int j = 0; j < gs; ++j) { s += sc[g * gs + j]; q += sh[g * gs + j]; }
-        const float inv = 1.0f / (static_cast<float>(gs) * static_cast<float>(p.HW));
-        const float mean = s * inv;
-        const float var = fmaxf(q * inv - mean * mean, 0.f);
-        gm[g] = mean; gr[g] = rsqrtf(var + p.eps);
-    }
-    __syncthreads();
+    groupnorm_scale_shift(p, b, sc, sh, gm, gr);
     const int vpp = C >> 2;                       // 4-channel vectors per pixel
     const int kpix = blockDim.x / vpp;            // pixels covered by the block per step
     const int c = (threadIdx.x % vpp) << 2;       // this thread's channels (constant)
     const int lp = threadIdx.x / vpp;             // this thread's pixel lane
     float k4[4], s4[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int g = (c + j) / gs;
-        const float k = gr[g] * __ldg(&p.gamma[c + j]);
-        k4[j] = k; s4[j] = __ldg(&p.beta[c + j]) - gm[g] * k;
-    }
+    for (int j = 0; j < 4; ++j) { k4[j] = sc[c + j]; s4[j] = sh[c + j]; }
     const bool from0 = c < p.C0;
     const float* src = from0 ? p.src0 + c : p.src1 + (c - p.C0);
     const int cs = from0 ? p.C0 : p.C1;

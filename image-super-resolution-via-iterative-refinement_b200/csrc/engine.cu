@@ -19,7 +19,7 @@
 #include "../../include/sr3_b200.h"
 #include "aux_kernels.cuh"
 #include "attn_tcgen05.cuh"
-#include "wgrad_tcgen05.cuh"
+#include "step_megakernel.cuh"
 
 using namespace sr3;
 typedef __nv_bfloat16 bf16;
@@ -130,7 +130,7 @@ struct GemmDesc {
     float* out_f32 = nullptr; OutSpec os{};
     bf16* out_bf16 = nullptr; OutSpec hs{};
     bf16* out_t = nullptr; int t_col0 = 0, t_rows = 0, t_ld = 0, t_per = 1;   // transposed bf16 store of columns >= t_col0
-    float* stats = nullptr; int stats_C = 0, stats_coff = 0;
+    double* stats = nullptr; int stats_C = 0, stats_coff = 0;
     const StepCtl* ctl = nullptr; PostParams post{};
 };
 
@@ -215,7 +215,18 @@ struct DevAllocs {
 };
 
 typedef std::function<void(cudaStream_t)> Op;
-struct GemmHandle { std::shared_ptr<GemmParams> p; const void* w_ptr = nullptr; long long w_bytes = 0; bool w_is_param = false; };
+struct GemmHandle { std::shared_ptr<GemmParams> p; const void* w_ptr = nullptr; long long w_bytes = 0; bool w_is_param = false; int bn = 0, mh = 0; };
+// One op of the persistent step kernel (step_megakernel.cuh), recorded next to the per-layer launch it replaces.
+struct MegaRec { int type = 0, variant = 0; std::shared_ptr<GemmParams> gp; std::vector<uint8_t> raw; };
+static thread_local std::vector<MegaRec>* g_mega_registry = nullptr;
+template <typename T>
+void mega_record(int type, const T& params) {
+    if (!g_mega_registry) return;
+    MegaRec r; r.type = type;
+    r.raw.resize((sizeof(T) + 3) & ~size_t(3));
+    memcpy(r.raw.data(), &params, sizeof(T));
+    g_mega_registry->push_back(std::move(r));
+}
 static thread_local std::vector<GemmHandle>* g_gemm_registry = nullptr;   // set by the engine while it builds its plan
 
 // Turns a GemmDesc into a launchable op (encodes the TMA maps, uploads the K-slab table).
@@ -305,6 +316,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.resid = d.resid; p.rs = d.rs; p.out_f32 = d.out_f32; p.os = d.os; p.out_bf16 = d.out_bf16; p.hs = d.hs;
     p.out_t = d.out_t; p.t_col0 = d.t_col0; p.t_rows = d.t_rows; p.t_ld = d.t_ld; p.t_per = d.t_per > 0 ? d.t_per : 1;
     p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
+    p.t_fixed = -1;
     if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
     // fp32 output / residual through smem + TMA: one 32-row x 32-column box per epilogue warp
     p.tma_epi = (d.mode == 0 && getenv("SR3_NO_TMA_EPI") == nullptr && (d.out_f32 || d.resid)) ? 1 : 0;
@@ -369,8 +381,12 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     REQUIRE((bn == 16 || bn == 32 || bn == 64 || bn == 128 || bn == 256) && (mh == 1 || (mh == 2 && bn <= 128 && bn != 32)), "unsupported tile %dx%d", 128 * mh, bn);
     std::shared_ptr<GemmParams> sp = std::make_shared<GemmParams>(p);
     if (g_gemm_registry) {
-        GemmHandle h; h.p = sp; h.w_ptr = d.b_ptr; h.w_bytes = 2LL * d.b_rows * d.b_K; h.w_is_param = d.b_is_param;
+        GemmHandle h; h.p = sp; h.w_ptr = d.b_ptr; h.w_bytes = 2LL * d.b_rows * d.b_K; h.w_is_param = d.b_is_param; h.bn = bn; h.mh = mh;
         g_gemm_registry->push_back(h);
+    }
+    if (g_mega_registry) {
+        MegaRec r; r.type = MOP_GEMM; r.variant = bn | (mh << 16); r.gp = sp;
+        g_mega_registry->push_back(std::move(r));
     }
     return [sp, grid, bn, mh, smem](cudaStream_t st) {
         const GemmParams& p = *sp;
@@ -403,12 +419,13 @@ Op make_attn_op(const bf16* qk, const bf16* vT, bf16* out, int nz, int Lt, int H
         const uint32_t box[2] = {64u, 128u};
         p.vt_map = encode_map(2, vT, dims, str, box);
     }
-    p.out = out; p.C = C; p.Lt = Lt; p.HW = HW;
+    p.out = out; p.C = C; p.Lt = Lt; p.HW = HW; p.nz = nz;
     p.dn = (C % 256 == 0) ? 256 : 128;
     p.scale_log2e = 1.4426950408889634f / sqrtf((float)C);
     static std::vector<int> seen;
     if (first_use_on_device(seen)) CK(cudaFuncSetAttribute(attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATTN_SMEM_BYTES));
     const dim3 grid((Lt / 128) * (C / p.dn), nz, 1);
+    mega_record(MOP_ATTN, p);
     return [p, grid](cudaStream_t st) { launch_k(attn_kernel, grid, dim3(ATTN_THREADS), ATTN_SMEM_BYTES, st, p); };
 }
 
@@ -543,7 +560,7 @@ void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, in
 
 // ------------------------------------------------------------------------------------------------ engine
 struct Act {
-    float* p = nullptr; float* stats = nullptr;
+    float* p = nullptr; double* stats = nullptr;
     int C = 0, H = 0, W = 0;
 };
 
@@ -577,7 +594,12 @@ struct sr3_engine {
 
     StepCtl* ctl_dev = nullptr;
     StepCtl ctl{};
-    float* stats_arena = nullptr; size_t stats_cap = 0, stats_used = 0;
+    double* stats_arena = nullptr; size_t stats_cap = 0, stats_used = 0;
+    // persistent step kernel (one cooperative launch per reverse step)
+    std::vector<MegaRec> mega;
+    bool use_mega = false;
+    MegaOp* mega_ops_dev = nullptr; uint8_t* mega_blob = nullptr; unsigned long long* mega_bar = nullptr; unsigned long long* mega_prof = nullptr;
+    std::vector<int> mega_types;
     bf16* in_buf = nullptr;
     float *x_state = nullptr, *eps_buf = nullptr, *mean_buf = nullptr, *noise_buf = nullptr, *nl_buf = nullptr, *io_a = nullptr, *io_b = nullptr;
     float *nl_table = nullptr, *post_tab = nullptr;
@@ -610,11 +632,11 @@ struct sr3_engine {
         REQUIRE(role_ptr.count(r) && role_max[r] >= bytes, "role buffer %s too small", r.c_str());
         return role_ptr[r];
     }
-    float* new_stats(int C) {
+    double* new_stats(int C) {
         const size_t n = (size_t)Bp * C * 2;
         if (dry) { stats_used += n; return nullptr; }
         REQUIRE(stats_used + n <= stats_cap, "stats arena overflow");
-        float* p = stats_arena + stats_used;
+        double* p = stats_arena + stats_used;
         stats_used += n;
         return p;
     }
@@ -705,6 +727,17 @@ struct sr3_engine {
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);
+        {   // the same op inside the persistent step kernel: B x items_per_image work items dealt contiguously to the CTAs
+            PrepParams m = p;
+            const int nth = GEMM_THREADS;
+            const int kp = vpp > nth ? 1 : nth / vpp;
+            int ipi = (4 * num_sms() + B / 2) / B; if (ipi < 1) ipi = 1;
+            int mp = (p.HW + ipi - 1) / ipi;
+            mp = ((mp + kp - 1) / kp) * kp;
+            if (mp > p.HW) mp = p.HW;
+            m.pix_per_block = mp; m.items_per_image = (p.HW + mp - 1) / mp; m.B = B;
+            mega_record(MOP_PREP, m);
+        }
         push([p, grid, smem, threads](cudaStream_t st) { launch_k(prep_kernel, grid, dim3(threads), (size_t)smem, st, p); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
     }
     void add_cast(const Act& s, bf16* dst, int up) {
@@ -815,6 +848,7 @@ struct sr3_engine {
         const int Lt = HW >= 128 ? HW : 128;            // tokens per attention batch (two 8x8 images share one)
         const int per = Lt / HW;                         // images per attention batch
         REQUIRE(Lt % 128 == 0 && (Bp % per) == 0, "attention geometry HW=%d", HW);
+        REQUIRE(C % 128 == 0, "%s: self-attention over %d channels is not supported (the q/k/v and P.v tiles are 128 columns wide; C must be a multiple of 128)", L.name.c_str(), C);
         const int nz = Bp / per;
         float* gn_w = f32_param(p + ".norm.weight", {C});
         float* gn_b = f32_param(p + ".norm.bias", {C});
@@ -874,6 +908,8 @@ struct sr3_engine {
                 const long long rows = (long long)nz * Lt;
                 const int blocks = (int)((rows + 7) / 8);
                 push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW); }, 3, 0, (double)rows * Lt * 6.0);
+                SoftmaxParams sp{}; sp.S = S; sp.P = P; sp.rows = rows; sp.L = Lt; sp.seg = HW;
+                mega_record(MOP_SOFTMAX, sp);
             }
             {   // O[z] = P v : rows = queries, N = head dim, K = keys
                 GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
@@ -945,7 +981,7 @@ struct sr3_engine {
             tau = static_cast<float*>(mem.alloc((size_t)Bp * inner * 4));
             // step prologue
             float4* sa = reinterpret_cast<float4*>(stats_arena);
-            const long long n4 = (long long)(stats_cap / 4);
+            const long long n4 = (long long)(stats_cap * sizeof(double) / 16);
             StepCtl* c = ctl_dev;
             push([=](cudaStream_t st) { launch_k(step_begin_kernel, dim3((int)std::min<long long>((n4 + 255) / 256, 592)), dim3(256), 0, st, sa, n4, c); });
             EmbedParams ep{}; ep.ctl = ctl_dev; ep.nl_table = nl_table; ep.nl_buf = nl_buf; ep.w1 = mlp_w1; ep.b1 = mlp_b1; ep.w2 = mlp_w2; ep.b2 = mlp_b2;
@@ -956,6 +992,8 @@ struct sr3_engine {
             float *fw = film_w, *fb = film_b, *fc = film_cb, *ta = tau, *fi = film; const int Fn = F, inn = inner;
             push([=](cudaStream_t st) { launch_k(film_kernel, dim3((Fn + 63) / 64), dim3(256), (size_t)((64 * (inn + 1) + Bn * inn) * 4), st, (const float*)fw, (const float*)fb, (const float*)fc, (const float*)ta, fi, Fn, inn, Bn); });
             side_end = (int)ops.size();
+            EmbedFilmParams fp{}; fp.e = ep; fp.wf = film_w; fp.bf = film_b; fp.cbias = film_cb; fp.film = film; fp.F = F; fp.B = B;
+            mega_record(MOP_EMBED_FILM, fp);
         }
 
         int film_off = 0;
@@ -1073,6 +1111,10 @@ struct sr3_engine {
                 d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
                 d.post.in_buf = in_buf; d.post.in_C = in_C; d.post.in_coff = cond_c;
                 push_gemm(d);
+                // the statistics arena is cleared for the NEXT step once nobody reads it any more (every GroupNorm apply has passed
+                // the grid barrier in front of the final conv)
+                ZeroParams zp{}; zp.ptr = reinterpret_cast<float4*>(stats_arena); zp.n4 = (long long)(stats_cap * sizeof(double) / 16);
+                mega_record(MOP_ZERO, zp);
             }
         }
     }
@@ -1098,7 +1140,7 @@ struct sr3_engine {
         build_plan();
         // allocate
         stats_cap = (stats_used + 3) & ~size_t(3);
-        stats_arena = static_cast<float*>(mem.alloc(stats_cap * sizeof(float)));
+        stats_arena = static_cast<double*>(mem.alloc(stats_cap * sizeof(double)));
         for (auto& kv : role_max) role_ptr[kv.first] = mem.alloc(kv.second);
         ctl_dev = static_cast<StepCtl*>(mem.alloc(sizeof(StepCtl)));
         in_buf = static_cast<bf16*>(mem.alloc((size_t)Bp * H * W * in_C * 2));
@@ -1112,8 +1154,10 @@ struct sr3_engine {
         // pass 2: real plan
         dry = false; stats_used = 0;
         g_gemm_registry = &gemms;
-        build_plan();
+        g_mega_registry = &mega;
+        try { build_plan(); } catch (...) { g_gemm_registry = nullptr; g_mega_registry = nullptr; throw; }
         g_gemm_registry = nullptr;
+        g_mega_registry = nullptr;
         if (getenv("SR3_NO_PREFETCH") == nullptr) {
             // every tile kernel pulls the weights of the next one into L2 (the last one those of the next step's first)
             for (size_t i = 0; i < gemms.size(); ++i) {
@@ -1125,10 +1169,64 @@ struct sr3_engine {
             }
         }
         CK(cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+        build_mega();
         CK(cudaDeviceSynchronize());
     }
 
+    // ---- persistent step kernel: serialise the recorded ops (parameter blocks 128-byte aligned) and upload them
+    void build_mega() {
+        use_mega = getenv("SR3_NO_MEGA") == nullptr && getenv("SR3_NO_FUSE_CAST") == nullptr && getenv("SR3_NO_FOLD_UP") == nullptr;
+        if (!use_mega) return;
+        std::vector<MegaOp> host_ops;
+        std::vector<uint8_t> blob;
+        for (size_t i = 0; i < mega.size(); ++i) {
+            MegaRec& r = mega[i];
+            MegaOp o{}; o.type = r.type; o.variant = r.variant;
+            const uint8_t* src = r.raw.data(); size_t n = r.raw.size();
+            if (r.type == MOP_GEMM) {
+                const int bn = r.variant & 0xffff, mh = r.variant >> 16;
+                if (!((bn == 16 || bn == 32 || bn == 64 || bn == 128) && (mh == 1 || mh == 2) && !(bn == 32 && mh == 2))) { use_mega = false; return; }
+                src = reinterpret_cast<const uint8_t*>(r.gp.get()); n = sizeof(GemmParams);
+            }
+            REQUIRE(n % 4 == 0 && n <= (size_t)(GEMM_HDR_BYTES - HDR_PARAMS), "step kernel: parameter block of %zu bytes does not fit the header", n);
+            // ops 0 (embedding + FiLM + nothing upstream) and 1 (first conv: reads the input buffer of the previous launch) and the final
+            // clear need no barrier; every other op consumes what all CTAs of its predecessor produced
+            o.sync_before = (i >= 2 && r.type != MOP_ZERO) ? 1 : 0;
+            o.param_bytes = (int)n;
+            blob.resize((blob.size() + 127) & ~size_t(127));
+            o.param_off = (long long)blob.size();
+            blob.insert(blob.end(), src, src + n);
+            host_ops.push_back(o);
+            mega_types.push_back(r.type);
+        }
+        REQUIRE(host_ops.size() >= 3 && mega[0].type == MOP_EMBED_FILM && mega[1].type == MOP_GEMM, "step kernel: unexpected plan head");
+        mega_ops_dev = static_cast<MegaOp*>(mem.alloc(host_ops.size() * sizeof(MegaOp), false));
+        mega_blob = static_cast<uint8_t*>(mem.alloc(blob.size(), false));
+        mega_bar = static_cast<unsigned long long*>(mem.alloc(128));
+        mega_prof = static_cast<unsigned long long*>(mem.alloc((host_ops.size() + 1) * sizeof(unsigned long long)));
+        REQUIRE((reinterpret_cast<uintptr_t>(mega_blob) & 127) == 0, "blob not 128B aligned");
+        CK(cudaMemcpy(mega_ops_dev, host_ops.data(), host_ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(mega_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+        static std::vector<int> seen;
+        if (first_use_on_device(seen)) CK(cudaFuncSetAttribute(step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel, GEMM_THREADS, SMEM_LIMIT));
+        REQUIRE(per_sm >= 1, "step kernel does not fit an SM");
+    }
+    void launch_mega(cudaStream_t st) {
+        MegaParams mp{};
+        mp.ops = mega_ops_dev; mp.n_ops = (int)mega_types.size(); mp.blob = mega_blob; mp.bar = mega_bar; mp.prof = mega_prof; mp.ctl = ctl_dev;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(num_sms()); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM_LIMIT; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;            // all CTAs co-resident: the grid barriers (and split-K meets) cannot deadlock
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = getenv("SR3_NO_COOP") ? 0 : 1;
+        CK(cudaLaunchKernelEx(&cfg, step_kernel, mp));
+    }
+
     void run_step(cudaStream_t st) {
+        if (use_mega) { launch_mega(st); return; }
         if (!use_graph) { for (auto& op : ops) op(st); return; }
         if (!graph) {
             cudaGraph_t g;
@@ -1430,10 +1528,32 @@ int sr3_engine_profile_step(sr3_engine* e, int t, int reps, int cap, int* kinds,
     }
     *n_ops = n;
     for (auto& x : ev) cudaEventDestroy(x);
+    // the per-layer path clears the statistics arena at the START of a step, the step kernel at the END of one: leave it clean
+    CK(cudaMemsetAsync(e->stats_arena, 0, e->stats_cap * sizeof(double), st));
+    CK(cudaStreamSynchronize(st));
     API_END
 }
 
-int sr3_engine_num_launches_per_step(const sr3_engine* e) { return e ? (int)e->ops.size() : 0; }
+int sr3_engine_uses_step_kernel(const sr3_engine* e) { return (e && e->use_mega) ? 1 : 0; }
+
+// Per-op device time of the most recent step-kernel launch (globaltimer stamps taken by CTA 0 after each grid barrier).
+int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, int* n_ops, void* stream) {
+    API_BEGIN
+    REQUIRE(e && types && us && n_ops, "null argument");
+    REQUIRE(e->use_mega, "this engine runs the per-layer path (SR3_NO_MEGA), there is no step kernel to profile");
+    const int n = (int)e->mega_types.size();
+    REQUIRE(cap >= n, "profile buffers too small (%d ops)", n);
+    CK(cudaSetDevice(e->dev));
+    CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+    std::vector<unsigned long long> ts(n + 1);
+    CK(cudaMemcpy(ts.data(), e->mega_prof, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { types[i] = e->mega_types[i]; us[i] = (double)(ts[i + 1] - ts[i]) * 1e-3; }
+    *n_ops = n;
+    API_END
+}
+
+int sr3_engine_num_launches_per_step(const sr3_engine* e) { return e ? (e->use_mega ? 1 : (int)e->ops.size()) : 0; }
+int sr3_engine_num_ops_per_step(const sr3_engine* e) { return e ? (int)e->ops.size() : 0; }
 int64_t sr3_engine_workspace_bytes(const sr3_engine* e) { return e ? e->mem.bytes : 0; }
 
 int sr3_engine_read_activation(sr3_engine* e, const char* name, float* dst, int64_t cap, int64_t* numel, int shape_bhwc[4], void* stream) {
@@ -1478,36 +1598,6 @@ int sr3_test_attention(const void* qk, const void* vT, void* out, int nz, int Lt
     API_END
 }
 
-// EXPERIMENTAL (training row): weight gradient of a stride-1 conv3x3 with MN-major tcgen05 operands (wgrad_tcgen05.cuh).
-int sr3_test_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, void* stream) {
-    API_BEGIN
-    REQUIRE(Cin % 64 == 0 && Cout % 64 == 0 && H % 8 == 0 && W % 8 == 0 && B >= 1, "bad test wgrad shape");
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    WgradParams p;
-    memset(&p, 0, sizeof(p));
-    auto mk = [&](const void* ptr, int C) {
-        const uint64_t dims[5] = {(uint64_t)C, (uint64_t)W, 1ull, (uint64_t)H, (uint64_t)B};
-        const uint64_t str[4] = {(uint64_t)C * 2, (uint64_t)W * C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
-        const uint32_t box[5] = {64u, 8u, 1u, 8u, 1u};
-        return encode_map(5, ptr, dims, str, box);
-    };
-    p.dy_map = mk(dy, Cout); p.x_map = mk(x, Cin);
-    p.dw = dw; p.Cin = Cin; p.Cout = Cout; p.H = H; p.W = W; p.B = B;
-    const int tiles_mn = ((Cout + 127) / 128) * (Cin / 64) * 3;
-    int slices = num_sms() / tiles_mn;                         // batch slices so that about one wave of CTAs runs
-    if (slices < 1) slices = 1;
-    if (slices > B) slices = B;
-    p.b_per_cta = (B + slices - 1) / slices;
-    slices = (B + p.b_per_cta - 1) / p.b_per_cta;
-    static std::vector<int> seen;
-    if (first_use_on_device(seen)) CK(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGRAD_SMEM_BYTES));
-    CK(cudaMemsetAsync(dw, 0, (size_t)Cout * 9 * Cin * sizeof(float), st));
-    wgrad_kernel<<<dim3(((Cout + 127) / 128) * (Cin / 64), 3, slices), dim3(WGRAD_THREADS), WGRAD_SMEM_BYTES, st>>>(p);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    API_END
-}
-
 int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int with_resid, int with_stats, int reps, float* ms_out) {
     API_BEGIN
     REQUIRE(ms_out && reps > 0, "bad arguments");
@@ -1518,7 +1608,7 @@ int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride
     bf16* wp = static_cast<bf16*>(mem.alloc((size_t)Cout * ktot * 2));
     float* y = static_cast<float*>(mem.alloc((size_t)B * OH * OW * Cout * 4));
     float* r = with_resid ? static_cast<float*>(mem.alloc((size_t)B * OH * OW * Cout * 4)) : nullptr;
-    float* st = with_stats ? static_cast<float*>(mem.alloc((size_t)B * Cout * 2 * 4)) : nullptr;
+    double* st = with_stats ? static_cast<double*>(mem.alloc((size_t)B * Cout * 2 * 8)) : nullptr;
     float* bias = static_cast<float*>(mem.alloc((size_t)Cout * 4));
     GemmDesc d; d.n_a = 1;
     d.a[0] = stride == 1 ? nhwc_src(x, B, H, W, Cin) : nhwc_stride2_src(x, B, H, W, Cin);
@@ -1558,7 +1648,7 @@ int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride
     API_END
 }
 
-int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin, int Cout,
+int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* y, double* stats, int B, int H, int W, int Cin, int Cout,
                   int ksize, int stride, void* stream) {
     API_BEGIN
     REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2) && Cin % 64 == 0 && Cout % 64 == 0, "bad test conv shape");
@@ -1582,6 +1672,31 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     d.stats = stats; d.stats_C = Cout;
     Op op = make_gemm_op(d, mem);
     op(st);
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
+// Test hook: conv (tile kernel, statistics in its epilogue) followed by the GroupNorm(+SiLU) apply pass, i.e. one Block of the
+// reference (GN -> Swish -> conv, unet.py:80-91) seen from the GN's side: y = conv(x) + bias, a = [silu](GN(y; gamma, beta)).
+int sr3_test_conv_groupnorm(const void* x, const float* w_oihw, const float* bias, const float* gamma, const float* beta, int groups, int silu,
+                            float* y, void* a_bf16, int B, int H, int W, int Cin, int Cout, int ksize, void* stream) {
+    API_BEGIN
+    REQUIRE((ksize == 1 || ksize == 3) && Cin % 64 == 0 && Cout % 64 == 0 && Cout % groups == 0, "bad test shape");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevAllocs mem;
+    double* stats = static_cast<double*>(mem.alloc((size_t)B * Cout * 2 * sizeof(double)));
+    int rc = sr3_test_conv(x, w_oihw, bias, y, stats, B, H, W, Cin, Cout, ksize, 1, stream);
+    if (rc) return rc;
+    PrepParams p{};
+    p.src0 = y; p.st0 = stats; p.C0 = Cout; p.C1 = 0;
+    p.gamma = gamma; p.beta = beta; p.groups = groups; p.HW = H * W; p.silu = silu; p.eps = 1e-5f;
+    p.out_a = static_cast<bf16*>(a_bf16); p.out_raw = nullptr;
+    const int vpp = Cout / 4;
+    REQUIRE(vpp <= 512, "too many channels");
+    const int kpix = vpp >= 256 ? 1 : 256 / vpp;
+    p.pix_per_block = kpix * 4; p.B = B; p.items_per_image = (p.HW + p.pix_per_block - 1) / p.pix_per_block;
+    const dim3 grid((p.HW + p.pix_per_block - 1) / p.pix_per_block, B);
+    launch_k(prep_kernel, grid, dim3(vpp * kpix), (size_t)((2 * Cout + 2 * groups) * sizeof(float)), st, p);
     CK(cudaStreamSynchronize(st));
     API_END
 }

@@ -117,10 +117,11 @@ struct GemmParams {
     // (the v third of the qkv projection lands directly as the K-major B operand v^T of O = P v)
     __nv_bfloat16* out_t;
     int t_col0, t_rows, t_ld, t_per;
-    float* stats;            // [B][stats_C][2] (sum, sumsq), channel offset stats_coff
+    double* stats;           // [B][stats_C][2] (sum, sumsq) in fp64, channel offset stats_coff (see stats_quantize)
     int stats_C, stats_coff;
     const StepCtl* ctl;
     PostParams post;
+    int t_fixed;             // >= 0: timestep of the running step (persistent step kernel: ctl->t_cur is not used there); -1: read ctl->t_cur
 };
 
 constexpr int GEMM_THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (two groups of four)
@@ -130,8 +131,14 @@ constexpr int GEMM_MAX_STAGES = 8;
 __host__ __device__ constexpr int gemm_epi_warp_bytes(bool resid) { return resid ? 12288 : 4096; }
 __host__ __device__ constexpr int gemm_epi_bytes(bool resid) { return GEMM_EPI_WARPS * gemm_epi_warp_bytes(resid); }
 constexpr int GEMM_MAX_K = 160;              // stages per tile (<= 3 K slabs each); the table is sized per launch
+// Shared-memory header (first 2 KB of the 1024-aligned region, same place for every op of the persistent step kernel):
+//   [0, 512) mbarriers | [512, 516) TMEM base slot | [520, 528) step scalars | [768, 2048) parameter block of the running op
+constexpr int GEMM_HDR_BYTES = 2048;
+constexpr int HDR_TMEM_SLOT = 512;
+constexpr int HDR_PARAMS = 768;
+constexpr int HDR_NUM_BARS = 64;
 __host__ __device__ constexpr int gemm_aux_bytes(int num_k) {
-    return 512 /*barriers*/ + ((num_k * 96 + 127) / 128) * 128 /*stage table*/ + GEMM_EPI_WARPS * 2 * 32 * 4 /*per-warp bias staging*/;
+    return GEMM_HDR_BYTES + ((num_k * 96 + 127) / 128) * 128 /*stage table*/ + GEMM_EPI_WARPS * 2 * 32 * 4 /*per-warp bias staging*/;
 }
 
 __host__ __device__ constexpr int gemm_stage_bytes(int block_n, int a_stage_bytes, int b_taps) { return a_stage_bytes + b_taps * block_n * 128; }
@@ -158,6 +165,12 @@ __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& z0, fl
     sincospif(2.0f * u2, &s, &c);
     z0 = r * c; z1 = r * s;
 }
+
+// GroupNorm statistics are accumulated with fp64 atomics.  Every contribution is first rounded to a multiple of 2^-20, so as long as
+// a sum stays below 2^33 (|x|_rms < 180 over a 512x512 channel) every addition is EXACT: the result does not depend on the order in
+// which the CTAs arrive -- repeat runs are bit identical -- and E[x^2] - mean^2 is evaluated in fp64 by the consumer (no fp32
+// cancellation for |mean| >> std).  The rounding itself is unbiased and ~1e-6 absolute per contribution, far below eps = 1e-5.
+__device__ __forceinline__ double stats_quantize(double v) { return rint(v * 1048576.0) * (1.0 / 1048576.0); }
 
 // Transposing warp reduction: every lane holds v[0..31] (one row, 32 columns); afterwards lane l returns the sum over the
 // 32 lanes (rows) of column l.  31 shuffles instead of 32 x 5.
@@ -191,7 +204,7 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
         for (int c = 0; c < q.C; ++c) q.eps_out[(static_cast<long long>(img) * q.C + c) * plane + pix] = eps[c];
         return;
     }
-    const int t = ctl.t_cur;
+    const int t = p.t_fixed >= 0 ? p.t_fixed : ctl.t_cur;
     const float c1 = q.tab[t], c2 = q.tab[q.T + t], pc1 = q.tab[2 * q.T + t], pc2 = q.tab[3 * q.T + t];
     const float sigma = (t > 0) ? expf(0.5f * q.tab[4 * q.T + t]) : 0.0f;
     float z[4] = {0.f, 0.f, 0.f, 0.f};
@@ -221,37 +234,43 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
     }
 }
 
-// Persistent, warp-specialised tile kernel (see the file header).
-template <int BLOCK_N, int MH>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
+static_assert(sizeof(GemmParams) <= GEMM_HDR_BYTES - HDR_PARAMS, "GemmParams must fit the shared-memory header");
+
+// Persistent, warp-specialised tile loop (see the file header).  Two callers:
+//   MEGA = false: gemm_tile_kernel, one launch per layer; `p` lives in the kernel parameter space, barriers / TMEM are set up here.
+//   MEGA = true : step_kernel (step_megakernel.cuh), the whole reverse step in ONE cooperative launch; `p` is the shared-memory copy
+//                 of the op's parameter block, `pm` its global-memory original (TMA descriptors must not live in shared memory),
+//                 TMEM was allocated once by the caller, `cta / ncta` replace blockIdx / gridDim.
+// `base` / `base_ptr`: 1024-aligned start of the CTA's dynamic shared memory (header first).
+template <int BLOCK_N, int MH, bool MEGA>
+__device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmParams* pm, const uint32_t base, uint8_t* base_ptr,
+                                               const uint32_t tmem_base_in, const int cta, const int ncta) {
     constexpr int B_BYTES = BLOCK_N * 128;
     constexpr uint32_t ACC_COLS = MH * BLOCK_N;                              // columns per accumulator buffer
     constexpr uint32_t TMEM_COLS = (2 * ACC_COLS) < 32 ? 32 : 2 * ACC_COLS;  // two buffers, power of two >= 32
     static_assert(TMEM_COLS <= 512 && (TMEM_COLS & (TMEM_COLS - 1)) == 0, "TMEM budget");
     constexpr uint32_t IDESC = umma_idesc_bf16(128, BLOCK_N);
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t raw = smem_u32(smem_raw);
-    const uint32_t base = (raw + 1023u) & ~1023u;
-    uint8_t* base_ptr = smem_raw + (base - raw);
     const int stages = p.stages;
     const int stage_bytes = p.a_stage_bytes + p.b_taps * B_BYTES;            // multiple of 1024
     const bool use_res_tma = p.tma_epi && p.resid != nullptr && p.ksplit <= 1;
     const int epi_warp_bytes = gemm_epi_warp_bytes(use_res_tma);
     const int epi_bytes = GEMM_EPI_WARPS * epi_warp_bytes;
-    const uint32_t epi_base = base + stages * stage_bytes;
-    const uint32_t bar_base = epi_base + epi_bytes;
+    const uint32_t bar_base = base;                                          // header
+    const uint32_t stage_base = base + GEMM_HDR_BYTES;
+    uint8_t* stage_ptr = base_ptr + GEMM_HDR_BYTES;
+    const uint32_t epi_base = stage_base + stages * stage_bytes;
     // barriers: full[8] empty[8] tmem_full[2] tmem_empty[2] res_full[4 warps]; then the TMEM slot
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (GEMM_MAX_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + a); };
     auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + 2 * w + b); };   // w in [0, 8)
-    uint8_t* aux_ptr = base_ptr + stages * stage_bytes + epi_bytes;
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(aux_ptr + 8 * (2 * GEMM_MAX_STAGES + 4 + 2 * GEMM_EPI_WARPS));
+    uint8_t* aux_ptr = stage_ptr + stages * stage_bytes + epi_bytes;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(base_ptr + HDR_TMEM_SLOT);
     // with ~227 KB of shared memory per CTA there is no L1 left: anything re-read per iteration must live in smem
-    StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr + 512);
-    float* bias_s = reinterpret_cast<float*>(aux_ptr + 512 + ((p.num_k * 96 + 127) / 128) * 128);
+    StageDesc* ktab_s = reinterpret_cast<StageDesc*>(aux_ptr);
+    float* bias_s = reinterpret_cast<float*>(aux_ptr + ((p.num_k * 96 + 127) / 128) * 128);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -264,10 +283,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         for (int i = threadIdx.x; i < p.num_k * 6; i += GEMM_THREADS) dst[i] = __ldg(&src[i]);
     }
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&p.a_map[0]);
-        tma_prefetch_desc(&p.a_map[1]);
-        tma_prefetch_desc(&p.b_map);
-        if (p.tma_epi) { tma_prefetch_desc(&p.out_map); tma_prefetch_desc(&p.res_map); }
+        tma_prefetch_desc(&pm->a_map[0]);
+        tma_prefetch_desc(&pm->a_map[1]);
+        tma_prefetch_desc(&pm->b_map);
+        if (p.tma_epi) { tma_prefetch_desc(&pm->out_map); tma_prefetch_desc(&pm->res_map); }
+        if constexpr (MEGA) {                    // the previous op's barriers (all quiescent: see the end of this function) are recycled
+            for (int i = 0; i < HDR_NUM_BARS; ++i) mbar_inval(bar_base + 8u * i);
+        }
         for (int s = 0; s < stages; ++s) {
             mbar_init(full_bar(s), 1);
             mbar_init(empty_bar(s), 1);
@@ -279,17 +301,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         for (int w = 0; w < GEMM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
         fence_mbar_init();
     }
-    if (warp == 1) {
-        tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
-        tmem_relinquish();
+    if constexpr (!MEGA) {
+        if (warp == 1) {
+            tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = MEGA ? tmem_base_in : *tmem_slot;
     if (warp == 2 && lane == 0 && p.pf_bytes > 0) {                   // L2 prefetch of this CTA's slice of the next layer's weights
-        long long chunk = ((p.pf_bytes + gridDim.x - 1) / gridDim.x + 15) & ~15ll;
-        const long long off = chunk * blockIdx.x;
+        long long chunk = ((p.pf_bytes + ncta - 1) / ncta + 15) & ~15ll;
+        const long long off = chunk * cta;
         if (off < p.pf_bytes) {
             if (off + chunk > p.pf_bytes) chunk = (p.pf_bytes - off) & ~15ll;
             const char* src = static_cast<const char*>(p.pf_ptr) + off;
@@ -299,8 +323,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             }
         }
     }
-    pdl_launch_dependents();      // the next kernel may be scheduled onto SMs as our CTAs retire ...
-    pdl_wait();                   // ... and we touch upstream activations / statistics only after the previous kernel completed
+    if constexpr (!MEGA) {
+        pdl_launch_dependents();  // the next kernel may be scheduled onto SMs as our CTAs retire ...
+        pdl_wait();               // ... and we touch upstream activations / statistics only after the previous kernel completed
+    }
 
     auto decode = [&](int tile_s, int& w0, int& h0, int& b0, int& n0, int& z) {
         const int tile = tile_s / ksplit;
@@ -314,8 +340,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         w0 = tw * p.w_box; h0 = th * p.h_box; b0 = tb * p.b_box + z * p.a_zstep; n0 = nt * BLOCK_N;
     };
     // contiguous tile range of this CTA (balanced to +-1 tile)
-    const int tile_begin = static_cast<int>((static_cast<long long>(total_tiles) * blockIdx.x) / gridDim.x);
-    const int tile_end = static_cast<int>((static_cast<long long>(total_tiles) * (blockIdx.x + 1)) / gridDim.x);
+    const int tile_begin = static_cast<int>((static_cast<long long>(total_tiles) * cta) / ncta);
+    const int tile_end = static_cast<int>((static_cast<long long>(total_tiles) * (cta + 1)) / ncta);
 
     if (warp == 0) {
         // ---------------------------------------------------- TMA producer warp (converged; one elected lane issues)
@@ -331,20 +357,34 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
                     const StageDesc& e = ktab_s[k];
-                    const uint32_t a_dst = base + s * stage_bytes;
+                    const uint32_t a_dst = stage_base + s * stage_bytes;
                     const int na = e.a_multi ? e.ntaps : 1;
                     mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : na * p.a_box_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
                     if (!(p.dbg & 8)) {
                         for (int t = 0; t < na; ++t)
-                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &p.a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
+                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &pm->a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
                                         h0 + e.tap[t].dh, b0);
                     }
                     if (!(p.dbg & 16)) {
                         for (int t = 0; t < e.ntaps; ++t)
-                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &p.b_map, full_bar(s), e.tap[t].b_col, brow);
+                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &pm->b_map, full_bar(s), e.tap[t].b_col, brow);
                     }
                 }
                 __syncwarp();
+                if (++s == stages) { s = 0; ph ^= 1u; }
+            }
+        }
+        if constexpr (MEGA) {
+            // tail: every stage this CTA filled has been released by the MMA warp's commit -> no arrival is in flight when the
+            // barriers are recycled by the next op
+            int filled = 0;
+            for (int tile = tile_begin; tile < tile_end; ++tile) {
+                const int sp = tile % ksplit;
+                filled += (p.num_k * (sp + 1)) / ksplit - (p.num_k * sp) / ksplit;
+            }
+            const int n_wait = filled < stages ? filled : stages;
+            for (int i = 0; i < n_wait; ++i) {
+                mbar_wait(empty_bar(s), ph ^ 1u, 6);
                 if (++s == stages) { s = 0; ph ^= 1u; }
             }
         }
@@ -352,7 +392,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         // ---------------------------------------------------- MMA issuer warp (converged; one elected lane issues)
         // descriptor low word = start address >> 4 (+ fixed LBO); byte offsets are added as (bytes >> 4)
         const uint64_t desc_hi = umma_desc_kmajor_sw128(0, 1024) & 0xFFFFFFFF00000000ull;
-        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_kmajor_sw128(base, 1024) & 0xFFFFFFFFull);
+        const uint32_t desc_lo0 = static_cast<uint32_t>(umma_desc_kmajor_sw128(stage_base, 1024) & 0xFFFFFFFFull);
         int s = 0, ti = 0;
         uint32_t ph = 0;
         for (int tile = tile_begin; tile < tile_end; ++tile, ++ti) {
@@ -396,7 +436,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         const int grp = ew >> 2;
         const uint32_t out_smem = epi_base + ew * epi_warp_bytes;           // 4 KB
         const uint32_t res_smem = out_smem + 4096;                          // 2 x 4 KB (layers with a residual only)
-        uint8_t* out_ptr = base_ptr + stages * stage_bytes + ew * epi_warp_bytes;
+        uint8_t* out_ptr = stage_ptr + stages * stage_bytes + ew * epi_warp_bytes;
         uint8_t* res_ptr = out_ptr + 4096;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const bool use_out_tma = p.tma_epi && p.out_f32 != nullptr;
@@ -405,9 +445,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
         bool out_pending = false;      // a bulk store from the staging buffer may still be reading it
         // GroupNorm partial sums of this lane's column, kept in registers across tiles of the same (image, column block)
         constexpr int NCHS = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;
-        float st_sum[NCHS], st_sq[NCHS];
+        double st_sum[NCHS], st_sq[NCHS];
 #pragma unroll
-        for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+        for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.0; st_sq[c] = 0.0; }
         int st_img = -1, st_n0 = -1;
         auto flush_stats = [&]() {
             if (st_img >= 0 && st_img < p.OB) {
@@ -415,14 +455,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 for (int c = 0; c < NCHS; ++c) {
                     const int n = st_n0 + c * 32 + lane;
                     if (n < p.n_valid) {
-                        float* st = p.stats + (static_cast<long long>(st_img) * p.stats_C + p.stats_coff + n) * 2;
-                        atomicAdd(st, st_sum[c]);
-                        atomicAdd(st + 1, st_sq[c]);
+                        double* st = p.stats + (static_cast<long long>(st_img) * p.stats_C + p.stats_coff + n) * 2;
+                        atomicAdd(st, stats_quantize(st_sum[c]));
+                        atomicAdd(st + 1, stats_quantize(st_sq[c]));
                     }
                 }
             }
 #pragma unroll
-            for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+            for (int c = 0; c < NCHS; ++c) { st_sum[c] = 0.0; st_sq[c] = 0.0; }
         };
         constexpr int NCH = BLOCK_N >= 32 ? BLOCK_N / 32 : 1;      // 32-column chunks per 128-row half
         constexpr int NITEMS = MH * NCH;                            // work items (half, chunk) per tile; this warp takes item % 2 == grp
@@ -445,7 +485,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                 item_geom(item, q, half, ch, sw, sh, c4);
                 const uint32_t b = res_count & 1;
                 mbar_arrive_expect_tx(res_bar(ew, b), 4096);
-                tma_load_5d(res_smem + b * 4096, &p.res_map, res_bar(ew, b), n0 + ch * 32, w0 + sw, 0, h0 + sh, c4);
+                tma_load_5d(res_smem + b * 4096, &pm->res_map, res_bar(ew, b), n0 + ch * 32, w0 + sw, 0, h0 + sh, c4);
             };
             const bool has_work = grp < NITEMS;
             if (use_res_tma && has_work && lane == 0) request_resid(grp);     // overlaps the main loop
@@ -465,7 +505,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         const int n = n0 + ch * 32 + lane;
                         if (n < p.n_valid) {
                             if (p.bias) bv += __ldg(&p.bias[n]);
-                            if (p.bias2) bv += __ldg(&p.bias2[static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride + n]);
+                            if (p.bias2) bv += __ldcg(&p.bias2[static_cast<long long>(img < p.OB ? img : 0) * p.bias2_stride + n]);   // written earlier in the same launch (step kernel): L2 only
                         }
                     }
                     bvs[ii] = bv;
@@ -503,7 +543,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             const uint64_t now = globaltimer_ns();
                             if (t0 == 0) t0 = now;
                             if (now - t0 > 4000000000ull) {
-                                printf("sr3: split-K wait timeout block=(%d,0,0) tile=%d counter=%u target=%u\n", blockIdx.x, tile, v, target);
+                                printf("sr3: split-K wait timeout cta=%d tile=%d counter=%u target=%u\n", cta, tile, v, target);
                                 __trap();
                             }
                         }
@@ -562,7 +602,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                             if (p.bias) bv += __ldg(&p.bias[n]);
                             if (p.bias2) {
                                 const int img0 = b0 + (half * 128 + qq * 32) / (p.w_box * p.h_box);
-                                bv += __ldg(&p.bias2[static_cast<long long>(img0 < p.OB ? img0 : 0) * p.bias2_stride + n]);
+                                bv += __ldcg(&p.bias2[static_cast<long long>(img0 < p.OB ? img0 : 0) * p.bias2_stride + n]);
                             }
                         }
                     } else {
@@ -652,7 +692,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                     } else if (row_ok && p.resid) {
                         const long long ro = out_index(p.rs, z, img, oh, ow);
                         for (int j = 0; j < 32; ++j)
-                            if (nb + j < p.n_valid) f[j] += p.resid[ro + nb + j];
+                            if (nb + j < p.n_valid) f[j] += __ldcg(&p.resid[ro + nb + j]);
                     }
                     if (p.dbg & 4) {
                     } else if (use_out_tma) {
@@ -667,7 +707,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_5d(&p.out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
+                            tma_store_5d(&pm->out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
                             tma_store_commit();
                         }
                         out_pending = true;
@@ -710,18 +750,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                         }
                     }
                     if (p.stats && !(p.dbg & 2)) {
-                        float cs, cq;
+                        double cs, cq;
                         if (use_out_tma && !(p.dbg & 4)) {
                             // the 32x32 tile sits in the (swizzled) staging buffer: lane c walks down column c -- conflict free, and a
                             // third of the instructions of the shuffle transposition below
                             const unsigned int okm = __ballot_sync(0xffffffffu, row_ok);
                             const uint8_t* colp = out_ptr + ((lane & 3) << 2);
                             const int cq4 = lane >> 2;
+                            // shifted sums: the fp32 partial sums run over x - x[row 0] (values of the size of the spread, not of the
+                            // mean), the shift is put back in fp64:  sum x = a + n s,  sum x^2 = q + 2 s a + n s^2
+                            const float sft = *reinterpret_cast<const float*>(colp + (cq4 << 4));
                             float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
                             for (int r = 0; r < 32; r += 2) {
-                                float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4));
-                                float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4));
+                                float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4)) - sft;
+                                float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4)) - sft;
                                 if (okm != 0xffffffffu) {
                                     if (!((okm >> r) & 1u)) x0 = 0.f;
                                     if (!((okm >> (r + 1)) & 1u)) x1 = 0.f;
@@ -729,7 +772,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 a0 += x0; q0 = fmaf(x0, x0, q0);
                                 a1 += x1; q1 = fmaf(x1, x1, q1);
                             }
-                            cs = a0 + a1; cq = q0 + q1;
+                            const double n_ok = static_cast<double>(__popc(okm)), ds = static_cast<double>(sft);
+                            const double da = static_cast<double>(a0 + a1), dq = static_cast<double>(q0 + q1);
+                            cs = da + n_ok * ds;
+                            cq = dq + 2.0 * ds * da + n_ok * ds * ds;
                         } else {
                             float s2[32];
 #pragma unroll
@@ -737,8 +783,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
                                 const float x = row_ok ? f[j] : 0.f;
                                 f[j] = x; s2[j] = x * x;
                             }
-                            cs = warp_column_sums(f);
-                            cq = warp_column_sums(s2);
+                            cs = static_cast<double>(warp_column_sums(f));
+                            cq = static_cast<double>(warp_column_sums(s2));
                         }
 #pragma unroll
                         for (int c = 0; c < NCHS; ++c)
@@ -749,11 +795,31 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid
             }       // pass
         }           // tiles
         if (p.stats && !(p.dbg & 2)) flush_stats();
-        if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
+        if constexpr (MEGA) {
+            // the consumer is a later op of the SAME launch (other CTAs, after a grid barrier): the bulk stores must be complete in
+            // global memory, not merely done reading shared memory
+            if (use_out_tma && out_pending && lane == 0) tma_store_wait_all<0>();
+        } else {
+            if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
+        }
+    }
+    if constexpr (MEGA) {
+        __threadfence();
+        fence_proxy_async_all();      // st.global results are read through TMA by the next op; its TMA loads also overwrite smem we touched
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (!MEGA) {
+        if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BLOCK_N, int MH>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tile_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    gemm_tile_body<BLOCK_N, MH, false>(p, &p, base, smem_raw + (base - raw), 0u, blockIdx.x, gridDim.x);
 }
 
 }  // namespace sr3

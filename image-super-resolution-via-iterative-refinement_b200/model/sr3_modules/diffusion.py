@@ -136,6 +136,14 @@ class GaussianDiffusion(nn.Module):
         """diffusion.py:221-246 (loss VALUE through the native UNet; the backward pass is the next milestone)."""
         x_start = x_in["HR"]
         b = x_start.shape[0]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.denoise_fn.parameters()):
+            # reference model.py:48-58 calls l_pix.backward() on this value; the native path has no backward yet -- say so HERE instead of
+            # letting autograd fail later with "element 0 of tensors does not require grad"
+            raise NotImplementedError(
+                "sr3_b200: p_losses / forward compute the loss VALUE only (no autograd graph, Dropout not applied): training "
+                "(optimize_parameters) is not implemented. Wrap the call in torch.no_grad() to evaluate the loss.")
+        if self.training and getattr(self.denoise_fn, "dropout", 0):
+            raise NotImplementedError("sr3_b200: training-mode Dropout (p=%g) is not implemented; call .eval() first" % self.denoise_fn.dropout)
         t = np.random.randint(1, self.num_timesteps + 1)
         gamma = torch.FloatTensor(np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1], self.sqrt_alphas_cumprod_prev[t], size=b)).to(x_start.device)
         gamma = gamma.view(b, -1)

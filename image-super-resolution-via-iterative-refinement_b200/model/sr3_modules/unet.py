@@ -115,6 +115,7 @@ class UNet(nn.Module):
         self._engines: Dict[tuple, "_native.Engine"] = {}
         self._engine_versions: Dict[tuple, int] = {}
         self._schedule = None
+        self._manual_version = 0
 
     # torch's default Conv2d / Linear initialisation, drawn in the reference's construction order so that
     # torch.manual_seed(s) yields bit-identical weights in both implementations.
@@ -146,8 +147,20 @@ class UNet(nn.Module):
                 sd[key].zero_()
 
     # ---- native engine management
+    MAX_ENGINES = 4          # distinct (batch, device, ...) engines kept alive; least recently used ones are released
+
     def _weights_version(self):
-        return sum(p._version for p in self.parameters())
+        return sum(p._version for p in self.parameters()) + self._manual_version
+
+    def invalidate(self):
+        """Force every engine to re-pack the weights before its next use.  Needed after updates that bypass autograd's version counter
+        (`p.data.copy_()`, EMA helpers, reference-style `m.weight.data` initialisers); `load_state_dict` and optimizer steps are seen
+        automatically."""
+        self._manual_version += 1
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        super()._load_from_state_dict(*args, **kwargs)
+        self._manual_version += 1
 
     def set_schedule(self, buffers, sqrt_alphas_cumprod_prev):
         self._schedule = ({k: v.detach().cpu().clone() for k, v in buffers.items()}, sqrt_alphas_cumprod_prev.copy())
@@ -157,14 +170,17 @@ class UNet(nn.Module):
     def engine(self, batch, conditional=True, channels=3):
         dev = next(self.parameters()).device
         key = (batch, str(dev), bool(conditional), channels)
-        eng = self._engines.get(key)
+        eng = self._engines.pop(key, None)
         if eng is None:
+            while len(self._engines) >= self.MAX_ENGINES:            # dicts keep insertion order: the first key is the least recently used
+                old = next(iter(self._engines))
+                del self._engines[old], self._engine_versions[old]
             cfg = dict(self.arch, channels=channels, conditional=conditional)
             eng = _native.Engine(cfg, batch, dev)
-            self._engines[key] = eng
             self._engine_versions[key] = -1
             if self._schedule is not None:
                 eng.set_schedule(*self._schedule)
+        self._engines[key] = eng                                     # (re-)insert as most recently used
         ver = self._weights_version()
         if self._engine_versions[key] != ver:
             eng.load_state_dict(self.state_dict())

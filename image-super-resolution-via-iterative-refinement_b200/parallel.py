@@ -54,14 +54,21 @@ def sharded_sample(sample_fn: Callable[[Optional[torch.Tensor], torch.Tensor, in
 
 
 def sharded_super_resolution(netG, x_in: torch.Tensor, x_T: Optional[torch.Tensor] = None, seed: int = 0, group=None) -> torch.Tensor:
-    """Batch-sharded `GaussianDiffusion.super_resolution`: returns the [B,3,H,W] finished images on every rank."""
+    """Batch-sharded `GaussianDiffusion.super_resolution` (reference: model/sr3_modules/diffusion.py:176-210 run on GPU 0 only,
+    model/model.py:60-78): returns the [B,3,H,W] finished images x_0 on every rank.
+
+    `x_in` / `x_T` are the GLOBAL (host or device) tensors; each rank copies and samples only its slice; the Philox noise streams are keyed
+    by the global sample index (`first_index`), so the images do not depend on the number of ranks."""
     dev = netG.betas.device
     if x_T is None:
         g = torch.Generator().manual_seed(seed)
         x_T = torch.randn(tuple(x_in.shape), generator=g)
 
     def fn(c, xt, first):
-        out = netG.super_resolution(c.to(dev), continous=True, x_T=xt.to(dev), seed=seed, first_index=first)
-        return out[-c.shape[0]:]          # last snapshot = x_0 of every image of the shard
+        if c.shape[0] == 0:
+            return torch.empty((0,) + tuple(xt.shape[1:]), device=dev)
+        eng = netG._engine(c.shape[0])
+        final, _ = eng.p_sample_loop(c.to(dev, non_blocking=True), xt.to(dev, non_blocking=True), None, seed, first, want_snapshots=False)
+        return final
 
     return sharded_sample(fn, x_in, x_T, group)

@@ -106,7 +106,14 @@ int sr3_p_sample_steps(sr3_engine* e, int t_start, int steps, void* stream);
 int sr3_read_state(sr3_engine* e, float* x_out, void* stream);
 
 /* Introspection for tests / bench. */
-int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernels in the captured step graph */
+int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernel launches per reverse step: 1 with the persistent step kernel */
+int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the per-layer path (SR3_NO_MEGA=1 / sr3_engine_profile_step) */
+/* 1 when one reverse step (reference p_sample: diffusion.py:151-174, UNet.forward unet.py:235-259) runs as ONE persistent
+ * cooperative launch (csrc/step_megakernel.cuh), 0 when it runs as a CUDA graph of per-layer launches (SR3_NO_MEGA=1). */
+int sr3_engine_uses_step_kernel(const sr3_engine* e);
+/* Per-op device time (us) of the most recent step-kernel launch: globaltimer stamps taken by CTA 0 after each grid barrier.
+ * types: 0 tensor-core tile loop, 1 GroupNorm apply, 2 fused attention, 3 row softmax, 4 embedding + FiLM, 5 statistics clear. */
+int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, int* n_ops, void* stream);
 int64_t sr3_engine_workspace_bytes(const sr3_engine* e);
 /* Per-kernel timing of one eager (non-graph) reverse step at timestep t, averaged over `reps` repetitions after one warm-up,
  * CUDA events on `stream` around every launch.  kinds: 0 tensor-core tile kernel, 1 GroupNorm apply, 2 cast/upsample,
@@ -123,14 +130,16 @@ int sr3_test_gemm(const void* a_bf16, const void* b_bf16, float* d, int M, int N
 /* Test hook for the fused attention core (S = q k^T / sqrt(C), softmax per image, O = P v; unet.py:129-139): qk bf16 [nz*Lt][2C]
  * (q | k), vT bf16 [nz*C][Lt], out bf16 [nz*Lt][C]; Lt in {128, 256} keys per attention batch, HW tokens per image (Lt % HW == 0). */
 int sr3_test_attention(const void* qk_bf16, const void* vT_bf16, void* out_bf16, int nz, int Lt, int HW, int C, void* stream);
-/* EXPERIMENTAL test hook for the training row (not used by any product path): weight gradient of a stride-1 conv3x3,
- * dW[co][tap][ci] = sum_pixels dY[p][co] * X[p+tap][ci]  (the wgrad of nn.Conv2d in unet.py:87, model.py:53 backward);
- * dy bf16 NHWC [B,H,W,Cout], x bf16 NHWC [B,H,W,Cin], dw fp32 [Cout][9][Cin] (overwritten). */
-int sr3_test_wgrad(const void* dy_bf16, const void* x_bf16, float* dw, int B, int H, int W, int Cin, int Cout, void* stream);
 /* Stand-alone NHWC conv for unit tests: x bf16 [B,H,W,Cin], w fp32 OIHW [Cout,Cin,k,k] (k in {1,3}), stride in {1,2},
- * y fp32 [B,OH,OW,Cout]; stats (optional) fp32 [B,Cout,2] must be zeroed by the caller. */
-int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, float* stats, int B, int H, int W, int Cin,
+ * y fp32 [B,OH,OW,Cout]; stats (optional) fp64 [B,Cout,2] (sum, sum of squares per image and channel: the GroupNorm statistics of
+ * unet.py:84, accumulated with order-independent fp64 atomics) must be zeroed by the caller. */
+int sr3_test_conv(const void* x_bf16, const float* w_oihw, const float* bias, float* y, double* stats, int B, int H, int W, int Cin,
                   int Cout, int ksize, int stride, void* stream);
+
+/* Test hook for the GroupNorm path of a Block (unet.py:80-91): y = conv(x) + bias with the statistics taken in the conv epilogue, then
+ * a = [silu](GroupNorm(y; groups, gamma, beta, eps 1e-5)) as bf16 NHWC.  Shapes as sr3_test_conv (stride 1). */
+int sr3_test_conv_groupnorm(const void* x_bf16, const float* w_oihw, const float* bias, const float* gamma, const float* beta, int groups,
+                            int silu, float* y, void* a_bf16, int B, int H, int W, int Cin, int Cout, int ksize, void* stream);
 
 /* Timing harness for one conv shape on zero-filled buffers (kernel-tuning experiments): average ms over `reps` launches. */
 int sr3_bench_conv(int B, int H, int W, int Cin, int Cout, int ksize, int stride, int with_resid, int with_stats, int reps, float* ms_out);

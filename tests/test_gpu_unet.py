@@ -85,7 +85,7 @@ def test_tiny_p_mean_variance_and_loop(golden):
     assert rel(out, g["loop_continous"]) < 2 * BF16_TOL, rel(out, g["loop_continous"])
     last = net.super_resolution(g["cond"].cuda(), continous=False, x_T=g["x_T"].cuda(), noises=g["noises"].cuda())
     assert last.shape == (3, 32, 32)
-    assert rel(last, g["loop_continous"][-1]) < 2 * BF16_TOL
+    assert rel(last, g["loop_continous"][-1]) < BF16_TOL
 
 
 def test_tiny_p_losses(golden):
@@ -102,7 +102,7 @@ def test_philox_loop_is_deterministic_and_shard_invariant(golden):
     c, xT = g["cond"].cuda(), g["x_T"].cuda()
     a = net.super_resolution(c, continous=True, x_T=xT, seed=77)
     b = net.super_resolution(c, continous=True, x_T=xT, seed=77)
-    assert torch.equal(a, b) or rel(a, b) < 5e-3          # fp32 atomics in the GroupNorm sums are order dependent -> bf16 rounding flips
+    assert torch.equal(a, b)                              # order-independent GroupNorm sums + fixed-order split-K: repeat runs are bit identical
     # image 1 alone, addressed by its global index, reproduces the batched run (multi-GPU sharding invariant)
     s = net.super_resolution(c[1:], continous=True, x_T=xT[1:], seed=77, first_index=1)
     assert rel(s[-1], a[-1]) < 1e-2
@@ -172,7 +172,7 @@ def test_state_dict_roundtrip_and_reload():
     assert rel(e2, e1) > 0.1
     net2.load_state_dict(sd, strict=True)
     e3 = net2.denoise_fn(x, nl)
-    assert rel(e3, e1) < BF16_TOL      # not bit-identical: atomic-order noise in the GN sums flips bf16 roundings (~5e-3)
+    assert torch.equal(e3, e1)         # same weights, same inputs -> same bits (order-independent statistics)
 
 
 def test_tiny_unconditional_loop_matches_oracle():
@@ -191,7 +191,7 @@ def test_tiny_unconditional_loop_matches_oracle():
     out = net.p_sample_loop((2, 3, 32, 32), continous=True, x_T=x_T.cuda(), noises=noises.cuda())
     assert out.shape == ref.shape == (2 * (1 + 6), 3, 32, 32)
     assert torch.equal(out[:2].cpu(), x_T)
-    assert rel(out, ref) < 2 * BF16_TOL, rel(out, ref)
+    assert rel(out, ref) < BF16_TOL, rel(out, ref)
 
 
 def test_sharded_super_resolution_single_rank(golden):
@@ -202,3 +202,50 @@ def test_sharded_super_resolution_single_rank(golden):
     a = parallel.sharded_super_resolution(net, g["cond"], x_T=g["x_T"], seed=11)
     b = net.super_resolution(g["cond"].cuda(), continous=True, x_T=g["x_T"].cuda(), seed=11, first_index=0)[-2:]
     assert a.shape == (2, 3, 32, 32) and rel(a, b) < BF16_TOL
+
+
+@pytest.mark.parametrize("batch", [2, 3])
+def test_step_kernel_matches_per_layer_path_bit_for_bit(golden, batch, monkeypatch):
+    """One reverse step as ONE persistent cooperative launch (csrc/step_megakernel.cuh) against the same plan run as a CUDA graph of
+    per-layer launches (SR3_NO_MEGA=1): identical arithmetic, identical bits -- for eps and for a seeded 10-step loop."""
+    g = golden["tiny_diffusion"]
+    c = g["cond"][:batch] if batch <= g["cond"].shape[0] else torch.cat([g["cond"], g["cond"][:1]], 0)
+    xT = g["x_T"][:batch] if batch <= g["x_T"].shape[0] else torch.cat([g["x_T"], g["x_T"][:1]], 0)
+    outs = {}
+    for mode in ("mega", "layers"):
+        if mode == "layers":
+            monkeypatch.setenv("SR3_NO_MEGA", "1")
+        else:
+            monkeypatch.delenv("SR3_NO_MEGA", raising=False)
+        net = build(TINY_UNET, 32, 0, sched=g["sched"])
+        eng = net.denoise_fn.engine(batch)
+        assert eng.uses_step_kernel() == (mode == "mega")
+        assert eng.launches_per_step() == (1 if mode == "mega" else eng.ops_per_step())
+        x = torch.cat([c, xT], 1).cuda()
+        nl = torch.linspace(0.2, 0.9, batch).view(-1, 1).cuda()
+        eps = net.denoise_fn(x, nl)
+        loop = net.super_resolution(c.cuda(), continous=True, x_T=xT.cuda(), seed=5)
+        outs[mode] = (eps.cpu(), loop.cpu())
+        del eng, net
+    monkeypatch.delenv("SR3_NO_MEGA", raising=False)
+    assert torch.equal(outs["mega"][0], outs["layers"][0])
+    assert torch.equal(outs["mega"][1], outs["layers"][1])
+
+
+@pytest.mark.timeout(900)
+def test_full_config_is_bit_reproducible(golden):
+    """Full 16->128 config, batch 16: two evaluations on the same inputs give the same bits, and a 3-step seeded loop twice as well."""
+    g = golden["full_16_128"]
+    net = build(FULL_UNET, 128, 0)
+    B = 16
+    gen = torch.Generator().manual_seed(4)
+    cond = (torch.rand(B, 3, 128, 128, generator=gen) * 2 - 1).cuda()
+    xT = torch.randn(B, 3, 128, 128, generator=gen).cuda()
+    nl = torch.full((B, 1), 0.6).cuda()
+    e1 = net.denoise_fn(torch.cat([cond, xT], 1), nl)
+    e2 = net.denoise_fn(torch.cat([cond, xT], 1), nl)
+    assert torch.equal(e1, e2) and torch.isfinite(e1).all()
+    net.set_new_noise_schedule({"schedule": "linear", "n_timestep": 3, "linear_start": 1e-6, "linear_end": 1e-2}, "cuda")
+    a = net.super_resolution(cond, continous=True, x_T=xT, seed=3)
+    b = net.super_resolution(cond, continous=True, x_T=xT, seed=3)
+    assert torch.equal(a, b)

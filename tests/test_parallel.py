@@ -58,3 +58,47 @@ def test_sharded_sample_two_ranks_gloo(n):
         ret = m.dict()
         mp.spawn(_worker, args=(world, port, n, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+class _FakeEngine:
+    def __init__(self, n):
+        self.n = n
+
+    def p_sample_loop(self, c, xt, noises, seed, first, want_snapshots=True):
+        assert c.shape[0] == xt.shape[0] == self.n and noises is None and not want_snapshots
+        idx = torch.arange(first, first + self.n, dtype=torch.float32).view(-1, 1, 1, 1)
+        return c * 2 + xt + idx + float(seed), None
+
+
+class _FakeNet:
+    """Stands in for GaussianDiffusion on a CPU box: sharded_super_resolution only needs `.betas.device` and `._engine(batch)`."""
+    betas = torch.zeros(1)
+
+    def _engine(self, n):
+        return _FakeEngine(n)
+
+
+def _worker_sr(rank, world, port, n, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(0)
+        cond = torch.rand(n, 3, 4, 4, generator=g)
+        x_T = torch.randn(n, 3, 4, 4, generator=g)
+        out = parallel.sharded_super_resolution(_FakeNet(), cond, x_T=x_T, seed=5)
+        ref = cond * 2 + x_T + torch.arange(n, dtype=torch.float32).view(-1, 1, 1, 1) + 5.0
+        ret[rank] = bool(torch.equal(out, ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [16, 3])
+def test_sharded_super_resolution_two_ranks_gloo(n):
+    """The public multi-GPU entry point (shard by image -> per-rank engine loop keyed by the global sample index -> all-gather)."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_worker_sr, args=(world, port, n, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}
