@@ -122,6 +122,7 @@ struct GemmDesc {
     int ksplit_max = 1;                           // split-K allowed up to this factor (image convs with few output tiles)
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
+    int z_phase = 0; long long z_off_hi = 0, z_off_lo = 0;   // nz = 4 output phases of a folded upsample conv (gemm_tcgen05.cuh)
     // epilogue
     int mode = 0, OW = 0, OH = 1, OB = 1, n_valid = 0;
     float scale = 1.f;
@@ -317,6 +318,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.out_t = d.out_t; p.t_col0 = d.t_col0; p.t_rows = d.t_rows; p.t_ld = d.t_ld; p.t_per = d.t_per > 0 ? d.t_per : 1;
     p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
     p.t_fixed = -1;
+    p.z_phase = d.z_phase; p.z_off_hi = d.z_off_hi; p.z_off_lo = d.z_off_lo;
     if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
     // fp32 output / residual through smem + TMA: one 32-row x 32-column box per epilogue warp
     p.tma_epi = (d.mode == 0 && getenv("SR3_NO_TMA_EPI") == nullptr && (d.out_f32 || d.resid)) ? 1 : 0;
@@ -327,12 +329,16 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
             c4z = (o.sB == 0 && o.sZ != 0);
             const long long s4 = c4z ? o.sZ : o.sB;
             const uint64_t n4 = c4z ? (uint64_t)d.nz : (uint64_t)(d.tiles_b * d.b_box > d.OB ? d.tiles_b * d.b_box : d.OB);
-            const uint64_t dims[5] = {(uint64_t)d.n_valid, (uint64_t)d.OW, 1ull, (uint64_t)d.OH, n4};
+            uint64_t dims[5] = {(uint64_t)d.n_valid, (uint64_t)d.OW, 1ull, (uint64_t)d.OH, n4};
             uint64_t str[4];
             str[0] = (uint64_t)o.sW * 4;
             str[1] = str[0] * d.OW;
             str[2] = d.OH > 1 ? (uint64_t)o.sH * 4 : str[1];
             str[3] = s4 != 0 ? (uint64_t)s4 * 4 : str[2] * d.OH;
+            if (d.z_phase) {      // {2N (px, n), W, 2 (py), H, B}: phase (py, px) is coordinate 2 and an offset of px * N in coordinate 0
+                REQUIRE(d.z_off_lo == d.n_valid && o.sW == 2 * d.n_valid, "phase-batched output must be NHWC with 2x the width");
+                dims[0] = 2ull * d.n_valid; dims[2] = 2ull; str[1] = (uint64_t)d.z_off_hi * 4;
+            }
             const uint32_t box[5] = {32u, (uint32_t)w_sub, 1u, (uint32_t)h_sub, 1u};
             REQUIRE(d.n_valid >= 32, "TMA epilogue needs at least 32 output columns");
             return encode_map(5, ptr + o.off, dims, str, box, CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
@@ -436,7 +442,7 @@ int pick_block_n(int cout);
 // The tile shape (rows x BLOCK_N) and the split-K factor are chosen by a byte model of the per-CTA critical path: a CTA ingests
 // stages x (A box + B boxes) through TMA at a fixed ~47 B/clk, runs ceil(tiles * split / SMs) waves, and a split tile costs an extra
 // partial-tile store + reload + a grid-level handshake.  (Measured on B200: tools/gpu_splitk_sweep.py)
-void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid = false) {
+void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid = false, int nz = 1) {
     bool tall_ok = getenv("SR3_NO_TALL") == nullptr && OW >= 8 && OH >= 16, has3 = false;
     for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh != 0) has3 = true; }
     tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
@@ -486,7 +492,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
                 const Cand& c = cands[i];
                 if (cout % c.bn != 0) continue;
                 int hb, bb; geom(c.mh, hb, bb);
-                const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn);
+                const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn) * nz;
                 const long long stage_bytes = (c.mh == 2 ? 36864 : 18432) + 3ll * c.bn * 128;
                 int sp = 1;
                 const double cost = model(tiles, nstage, stage_bytes, c.mh * 128, c.bn, sp);
@@ -508,7 +514,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
         d.tall = 0; d.mh = 1;
         pick_image_box(OW, OH, d.w_box, d.h_box, d.b_box);
         d.block_n = pick_block_n(cout);
-        const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box);
+        const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box) * nz;
         if (getenv("SR3_BLOCK_N") == nullptr && cout % 32 == 0) {
             // generic stages group up to three K slabs (one A box + one B box each)
             const int nstage = ((int)d.slabs.size() + 2) / 3;
@@ -759,16 +765,18 @@ struct sr3_engine {
         Act out;
         bf16* raw_out = nullptr;          // also store bf16(out) (input of a following Down / Upsample conv): no separate cast pass
         bool custom_os = false; OutSpec os{};   // output addressing other than plain NHWC (phase of a folded upsample conv)
+        int nz = 1, b_zrows = 0, z_phase = 0; long long z_off_hi = 0, z_off_lo = 0;   // the four phases of a folded upsample conv in ONE launch
     };
     void add_conv(const ConvArgs& c) {
         if (dry) return;
         GemmDesc d;
         d.n_a = c.n_a; d.a[0] = c.a[0]; d.a[1] = c.a[1];
         d.slabs = c.slabs;
-        conv_geometry(d, c.OW, c.OH, Bp, c.cout, c.resid != nullptr);
-        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = ((c.cout + 127) / 128) * 128;      // weights are padded to 128 rows (new_weight)
+        conv_geometry(d, c.OW, c.OH, Bp, c.cout, c.resid != nullptr, c.nz);
+        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = (long long)c.nz * (((c.cout + 127) / 128) * 128);      // weights are padded to 128 rows (new_weight)
         d.b_is_param = true;
-        d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = 1;
+        d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = c.nz; d.a_zstep = 0; d.b_zrows = c.b_zrows;
+        d.z_phase = c.z_phase; d.z_off_hi = c.z_off_hi; d.z_off_lo = c.z_off_lo;
         d.OW = c.OW; d.OH = c.OH; d.OB = B; d.n_valid = c.cout;
         d.bias = c.bias; d.bias2 = c.bias2; d.bias2_stride = c.bias2_stride;
         d.resid = c.resid; d.rs = nhwc_out(c.OH, c.OW, c.cout);
@@ -1059,8 +1067,14 @@ struct sr3_engine {
                 // 3x3 taps that alias onto the same low-res pixel summed into one weight (exact in real arithmetic, 2.25x fewer
                 // MACs, no 4x-sized intermediate).  One GEMM per phase, each writing its quarter of the NHWC output.
                 const int C = x.C, Hl = x.H, Wl = x.W;
+                const int rows_pad = ((C + 127) / 128) * 128;
+                const bool merge = getenv("SR3_NO_MERGE_UP") == nullptr;        // all four phases in one launch / op (gemm-batch z = phase)
                 bf16* wf[4];
-                for (int ph = 0; ph < 4; ++ph) wf[ph] = new_weight(C, 4 * C, pick_block_n(C));
+                if (dry) { for (int ph = 0; ph < 4; ++ph) wf[ph] = nullptr; }
+                else {
+                    bf16* wall = static_cast<bf16*>(mem.alloc((size_t)4 * rows_pad * 4 * C * sizeof(bf16)));   // [phase][rows_pad][4C]
+                    for (int ph = 0; ph < 4; ++ph) wf[ph] = wall + (size_t)ph * rows_pad * 4 * C;
+                }
                 if (!dry) {
                     bf16* w0 = wf[0]; bf16* w1 = wf[1]; bf16* w2 = wf[2]; bf16* w3 = wf[3];
                     add_param(L.name + ".conv.weight", {C, C, 3, 3}, [=](const float* src, cudaStream_t st) {
@@ -1073,7 +1087,7 @@ struct sr3_engine {
                 bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2));
                 if (!fuse_cast) add_cast(x, raw, 1);
                 Act y = new_act(C, Hl * 2, Wl * 2, L.name);
-                for (int ph = 0; ph < 4; ++ph) {
+                for (int ph = 0; ph < (merge ? 1 : 4); ++ph) {
                     const int py = ph >> 1, px = ph & 1;
                     ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(raw, Bp, Hl, Wl, C);
                     for (int a = 0; a < 2; ++a)
@@ -1085,6 +1099,7 @@ struct sr3_engine {
                     c.w = wf[ph]; c.ktot = 4 * C; c.cout = C; c.OH = Hl; c.OW = Wl; c.bias = b; c.out = y;
                     c.custom_os = true;
                     c.os.sZ = 0; c.os.sB = 4LL * Hl * Wl * C; c.os.sH = 4LL * Wl * C; c.os.sW = 2LL * C; c.os.off = (long long)py * 2 * Wl * C + (long long)px * C;
+                    if (merge) { c.nz = 4; c.b_zrows = rows_pad; c.z_phase = 1; c.z_off_hi = 2LL * Wl * C; c.z_off_lo = C; }
                     add_conv(c);
                 }
                 x = y;

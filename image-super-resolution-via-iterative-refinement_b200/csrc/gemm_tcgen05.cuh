@@ -121,6 +121,11 @@ struct GemmParams {
     int stats_C, stats_coff;
     const StepCtl* ctl;
     PostParams post;
+    // z_phase = 1: the gemm-batch index z = 2*py + px is the output phase of a folded (nearest-2x -> conv3x3): taps shift by (py, px) input
+    // pixels, weights of phase z start at row z * b_zrows, the tile lands at output pixel (2h + py, 2w + px) -- out_map is then
+    // {2N (px, n), W, 2 (py), H, B} and plain stores add (py * z_off_hi + px * z_off_lo) elements
+    int z_phase;
+    long long z_off_hi, z_off_lo;
     int t_fixed;             // >= 0: timestep of the running step (persistent step kernel: ctl->t_cur is not used there); -1: read ctl->t_cur
 };
 
@@ -236,6 +241,43 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
 
 static_assert(sizeof(GemmParams) <= GEMM_HDR_BYTES - HDR_PARAMS, "GemmParams must fit the shared-memory header");
 
+// CTA-local set-up of one tile-kernel op: stage table -> shared memory, TMA descriptor prefetch, mbarrier (re-)initialisation.  Nothing here
+// depends on data produced by other CTAs, so the persistent step kernel runs it BEFORE waiting at the grid barrier in front of the op.
+// Must be followed by a block-wide barrier.
+__device__ __forceinline__ void gemm_stage_setup(const GemmParams& p, const GemmParams* pm, const uint32_t base, uint8_t* base_ptr, const int block_n,
+                                                 const bool recycle) {
+    const int stages = p.stages;
+    const int stage_bytes = p.a_stage_bytes + p.b_taps * block_n * 128;
+    const bool use_res_tma = p.tma_epi && p.resid != nullptr && p.ksplit <= 1;
+    const int epi_bytes = GEMM_EPI_WARPS * gemm_epi_warp_bytes(use_res_tma);
+    uint8_t* aux_ptr = base_ptr + GEMM_HDR_BYTES + stages * stage_bytes + epi_bytes;
+    {
+        const int4* src = reinterpret_cast<const int4*>(p.ktab);
+        int4* dst = reinterpret_cast<int4*>(aux_ptr);
+        for (int i = threadIdx.x; i < p.num_k * 6; i += blockDim.x) dst[i] = __ldg(&src[i]);
+    }
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&pm->a_map[0]);
+        tma_prefetch_desc(&pm->a_map[1]);
+        tma_prefetch_desc(&pm->b_map);
+        if (p.tma_epi) { tma_prefetch_desc(&pm->out_map); tma_prefetch_desc(&pm->res_map); }
+        const uint32_t bar_base = base;
+        if (recycle) {                           // the previous op's barriers (all quiescent: see the end of gemm_tile_body) are recycled
+            for (int i = 0; i < HDR_NUM_BARS; ++i) mbar_inval(bar_base + 8u * i);
+        }
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(bar_base + 8u * s, 1);                                     // full
+            mbar_init(bar_base + 8u * (GEMM_MAX_STAGES + s), 1);                 // empty
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(bar_base + 8u * (2 * GEMM_MAX_STAGES + a), 1);             // tmem full
+            mbar_init(bar_base + 8u * (2 * GEMM_MAX_STAGES + 2 + a), GEMM_EPI_WARPS);   // tmem empty: one arrive per epilogue warp
+        }
+        for (int w = 0; w < 2 * GEMM_EPI_WARPS; ++w) mbar_init(bar_base + 8u * (2 * GEMM_MAX_STAGES + 4 + w), 1);   // residual tiles
+        fence_mbar_init();
+    }
+}
+
 // Persistent, warp-specialised tile loop (see the file header).  Two callers:
 //   MEGA = false: gemm_tile_kernel, one launch per layer; `p` lives in the kernel parameter space, barriers / TMEM are set up here.
 //   MEGA = true : step_kernel (step_megakernel.cuh), the whole reverse step in ONE cooperative launch; `p` is the shared-memory copy
@@ -277,38 +319,17 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int total_tiles = tiles_m * p.n_tiles * p.nz * ksplit;      // split index fastest: the CTAs of one output tile run together
-    {
-        const int4* src = reinterpret_cast<const int4*>(p.ktab);
-        int4* dst = reinterpret_cast<int4*>(ktab_s);
-        for (int i = threadIdx.x; i < p.num_k * 6; i += GEMM_THREADS) dst[i] = __ldg(&src[i]);
-    }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&pm->a_map[0]);
-        tma_prefetch_desc(&pm->a_map[1]);
-        tma_prefetch_desc(&pm->b_map);
-        if (p.tma_epi) { tma_prefetch_desc(&pm->out_map); tma_prefetch_desc(&pm->res_map); }
-        if constexpr (MEGA) {                    // the previous op's barriers (all quiescent: see the end of this function) are recycled
-            for (int i = 0; i < HDR_NUM_BARS; ++i) mbar_inval(bar_base + 8u * i);
-        }
-        for (int s = 0; s < stages; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
-        }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), GEMM_EPI_WARPS);   // one arrive per epilogue warp
-        }
-        for (int w = 0; w < GEMM_EPI_WARPS; ++w) { mbar_init(res_bar(w, 0), 1); mbar_init(res_bar(w, 1), 1); }
-        fence_mbar_init();
-    }
+    if constexpr (!MEGA) gemm_stage_setup(p, pm, base, base_ptr, BLOCK_N, false);     // (the step kernel did this before its grid barrier)
     if constexpr (!MEGA) {
         if (warp == 1) {
             tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_slot)), TMEM_COLS);
             tmem_relinquish();
         }
     }
-    tc_fence_before();
-    __syncthreads();
+    if constexpr (!MEGA) {
+        tc_fence_before();
+        __syncthreads();
+    }
     tc_fence_after();
     const uint32_t tmem_base = MEGA ? tmem_base_in : *tmem_slot;
     if (warp == 2 && lane == 0 && p.pf_bytes > 0) {                   // L2 prefetch of this CTA's slice of the next layer's weights
@@ -351,6 +372,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             int w0, h0, b0, n0, z;
             decode(tile, w0, h0, b0, n0, z);
             const int brow = n0 + z * p.b_zrows;
+            const int zdw = p.z_phase ? (z & 1) : 0, zdh = p.z_phase ? (z >> 1) : 0;
             const int sp = tile % ksplit;
             const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
@@ -362,8 +384,8 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                     mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : na * p.a_box_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
                     if (!(p.dbg & 8)) {
                         for (int t = 0; t < na; ++t)
-                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &pm->a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw, e.tap[t].p,
-                                        h0 + e.tap[t].dh, b0);
+                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &pm->a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw + zdw, e.tap[t].p,
+                                        h0 + e.tap[t].dh + (e.a_multi ? zdh : 0), b0);     // tall halo boxes always start one row above the tile
                     }
                     if (!(p.dbg & 16)) {
                         for (int t = 0; t < e.ntaps; ++t)
@@ -400,6 +422,11 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             mbar_wait(tempty_bar(acc), ((ti >> 1) & 1) ^ 1u, 4);        // epilogue has drained this accumulator
             tc_fence_after();
             const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+            int zrow_off = 0;                                           // folded-upsample phase py: vertical taps one halo row further down
+            if (p.z_phase) {
+                const int zz = (tile / ksplit) / (tiles_m * p.n_tiles);
+                zrow_off = (zz >> 1) * 1024;
+            }
             const int sp = tile % ksplit;
             const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
@@ -413,7 +440,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
 #pragma unroll
                         for (int half = 0; half < MH; ++half) {
                             for (int t = 0; t < e.ntaps; ++t) {
-                                const uint64_t adesc = desc_hi | (a_lo + ((half * p.a_half_off + e.tap[t].a_off) >> 4));
+                                const uint64_t adesc = desc_hi | (a_lo + ((half * p.a_half_off + e.tap[t].a_off + (e.a_multi ? 0 : zrow_off)) >> 4));
                                 const uint64_t bdesc = desc_hi | (b_lo + ((t * B_BYTES) >> 4));
 #pragma unroll
                                 for (int kk = 0; kk < 4; ++kk)   // 4 x UMMA_K(16) = 64 channels; +32 B inside the 128 B swizzle row
@@ -707,12 +734,13 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                         fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            tma_store_5d(&pm->out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
+                            if (p.z_phase) tma_store_5d(&pm->out_map, out_smem, (z & 1) * p.n_valid + nb, w0 + sw, z >> 1, h0 + sh, c4);
+                            else tma_store_5d(&pm->out_map, out_smem, nb, w0 + sw, 0, h0 + sh, c4);
                             tma_store_commit();
                         }
                         out_pending = true;
                     } else if (row_ok && p.out_f32) {
-                        const long long oo = out_index(p.os, z, img, oh, ow);
+                        const long long oo = out_index(p.os, z, img, oh, ow) + (p.z_phase ? (z >> 1) * p.z_off_hi + (z & 1) * p.z_off_lo : 0);
                         if (full) {
                             float4* o4 = reinterpret_cast<float4*>(p.out_f32 + oo + nb);
 #pragma unroll

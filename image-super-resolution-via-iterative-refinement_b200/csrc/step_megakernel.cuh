@@ -58,13 +58,18 @@ struct GridBarrier {
             target = v - (v % ncta);
         }
     }
-    // all threads of the CTA; everything written by this CTA before the call is visible to every CTA after it returns
-    __device__ __forceinline__ void sync(int tag) {
+    // Split barrier.  arrive(): all threads of the CTA; everything this CTA wrote before is published.  wait(): returns once every CTA has
+    // arrived; what they published is visible to all threads of this CTA afterwards.  CTA-local set-up of the next op goes in between.
+    __device__ __forceinline__ void arrive() {
         __syncthreads();
         if (threadIdx.x == 0) {
             target += n;
             __threadfence();
             red_release_gpu_add_u64(ctr, 1ull);
+        }
+    }
+    __device__ __forceinline__ void wait(int tag) {
+        if (threadIdx.x == 0) {
             uint64_t t0 = 0;
             for (uint32_t spins = 0;; ++spins) {
                 if (ld_acquire_gpu_u64(ctr) >= target) break;
@@ -286,16 +291,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_cons
     for (int i = 0; i < mp.n_ops; ++i) {
         const MegaOp op = mp.ops[i];
         const uint8_t* gparams = mp.blob + op.param_off;
-        if (op.sync_before) gb.sync(i);
-        if (mp.prof && cta == 0 && threadIdx.x == 0) mp.prof[i] = globaltimer_ns();
-        // parameter block -> shared-memory header (the previous op finished with a __syncthreads)
+        if (op.sync_before) gb.arrive();         // (starts with a __syncthreads: the previous op is finished in this CTA)
+        // CTA-local set-up, overlapped with the other CTAs still arriving: parameter block -> shared-memory header, and for a tile op its
+        // stage table / descriptor prefetch / mbarrier recycling
         for (int w = threadIdx.x; w < (op.param_bytes >> 2); w += blockDim.x)
             reinterpret_cast<uint32_t*>(hdr_params)[w] = __ldg(reinterpret_cast<const uint32_t*>(gparams) + w);
         __syncthreads();
+        if (op.type == MOP_GEMM) {
+            if (threadIdx.x == 0) reinterpret_cast<GemmParams*>(hdr_params)->t_fixed = t_step;
+            gemm_stage_setup(*reinterpret_cast<const GemmParams*>(hdr_params), reinterpret_cast<const GemmParams*>(gparams), base, base_ptr,
+                             op.variant & 0xffff, true);
+        }
+        if (op.sync_before) gb.wait(i); else __syncthreads();
+        if (mp.prof && cta == 0 && threadIdx.x == 0) mp.prof[i] = globaltimer_ns();
         switch (op.type) {
             case MOP_GEMM: {
-                if (threadIdx.x == 0) reinterpret_cast<GemmParams*>(hdr_params)->t_fixed = t_step;
-                __syncthreads();
                 switch (op.variant) {
                     case 16 | (1 << 16): mega_gemm<16, 1>(hdr_params, gparams, base, base_ptr, tmem_base, cta, ncta); break;
                     case 16 | (2 << 16): mega_gemm<16, 2>(hdr_params, gparams, base, base_ptr, tmem_base, cta, ncta); break;
