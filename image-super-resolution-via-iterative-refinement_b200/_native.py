@@ -19,7 +19,10 @@ class UNetConfigC(ctypes.Structure):
     _fields_ = [("in_channel", c_int), ("out_channel", c_int), ("inner_channel", c_int), ("norm_groups", c_int),
                 ("n_mults", c_int), ("channel_mults", c_int * SR3_MAX_LEVELS), ("n_attn_res", c_int),
                 ("attn_res", c_int * SR3_MAX_LEVELS), ("res_blocks", c_int), ("image_size", c_int), ("channels", c_int),
-                ("conditional", c_int)]
+                ("conditional", c_int), ("precision", c_int)]
+
+
+PRECISIONS = {"bf16": 0, "fp32": 1}          # "fp32" = precise mode: (hi, lo) bf16 operand pairs, three tensor-core passes
 
 
 _SIGS = {
@@ -125,6 +128,10 @@ class Engine:
         for i, a in enumerate(attn):
             c.attn_res[i] = a
         c.res_blocks, c.image_size, c.channels, c.conditional = cfg["res_blocks"], cfg["image_size"], cfg["channels"], int(cfg["conditional"])
+        self.precision = cfg.get("precision", "bf16")
+        if self.precision not in PRECISIONS:
+            raise ValueError("precision must be one of %s, got %r" % (sorted(PRECISIONS), self.precision))
+        c.precision = PRECISIONS[self.precision]
         self._h = c_void_p()
         idx = device.index if device.index is not None else torch.cuda.current_device()
         _check(lib().sr3_engine_create(ctypes.byref(c), batch, idx, ctypes.byref(self._h)))

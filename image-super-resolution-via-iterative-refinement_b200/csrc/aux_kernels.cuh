@@ -15,6 +15,16 @@ __device__ __forceinline__ uint2 pack_bf16x4(float a, float b, float c, float d)
     u.y = *reinterpret_cast<uint32_t*>(&hi);
     return u;
 }
+// precise mode: the part of x that bf16(x) loses, itself rounded to bf16 (x ~ hi + lo to ~2^-17 relative)
+__device__ __forceinline__ float bf16_residual(float x) { return x - __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ uint2 pack_bf16x4_residual(float a, float b, float c, float d) {
+    return pack_bf16x4(bf16_residual(a), bf16_residual(b), bf16_residual(c), bf16_residual(d));
+}
+// One 4-channel vector of a bf16 operand tensor: `o` = element offset of the high halves; precise mode (lo_off != 0) also stores the low halves
+__device__ __forceinline__ void store_operand4(__nv_bfloat16* base, long long o, long long lo_off, float a, float b, float c, float d) {
+    *reinterpret_cast<uint2*>(base + o) = pack_bf16x4(a, b, c, d);
+    if (lo_off) *reinterpret_cast<uint2*>(base + o + lo_off) = pack_bf16x4_residual(a, b, c, d);
+}
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm apply: a = [silu]( (x - mean_g) * rstd_g * gamma_c + beta_c ), x = concat(src0, src1) along channels.
@@ -30,6 +40,7 @@ struct PrepParams {
     __nv_bfloat16* out_a;                   // [B][HW][C0+C1]
     __nv_bfloat16* out_raw;                 // optional bf16(x), same shape
     int B, items_per_image;                 // persistent step kernel: work items = B x items_per_image blocks of pix_per_block pixels
+    int precise;                            // 1: operands are (hi | lo) pairs -- out rows are 2 (C0+C1) wide, low halves C0+C1 elements behind
 };
 
 // Per-(image, channel) scale / shift of a GroupNorm from the fp64 channel sums: y = x * sc[c] + sh[c].
@@ -101,9 +112,10 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
             if (pp < pix1) {
                 float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
                 if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                const long long o = (img + pp) * C + c;
-                *reinterpret_cast<uint2*>(p.out_a + o) = pack_bf16x4(y0, y1, y2, y3);
-                if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = pack_bf16x4(x[u].x, x[u].y, x[u].z, x[u].w);
+                const long long o = (img + pp) * (p.precise ? 2 * C : C) + c;
+                const long long lo_off = p.precise ? C : 0;
+                store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);
+                if (p.out_raw) store_operand4(p.out_raw, o, lo_off, x[u].x, x[u].y, x[u].z, x[u].w);
             }
         }
     }
@@ -134,7 +146,7 @@ __global__ void __launch_bounds__(256) cast_kernel(const float* __restrict__ src
 // Rows are grouped in segments of `seg` tokens; a row only attends to the keys of its own segment (two 64-token images share
 // one 128-row attention batch); keys outside get probability 0.
 __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ S, __nv_bfloat16* __restrict__ P, long long rows, int L,
-                                                      int seg) {
+                                                      int seg, int precise) {
     pdl_launch_dependents();
     pdl_wait();
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -143,7 +155,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
     const int r_in = static_cast<int>(row % L);
     const int k0 = (r_in / seg) * seg;
     const float* s = S + row * L;
-    __nv_bfloat16* pr = P + row * L;
+    __nv_bfloat16* pr = P + row * (precise ? 2 * L : L);
     float m = -INFINITY;
     for (int k = k0 + lane; k < k0 + seg; k += 32) m = fmaxf(m, s[k]);
 #pragma unroll
@@ -156,6 +168,7 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
     for (int k = lane; k < L; k += 32) {
         const float v = (k >= k0 && k < k0 + seg) ? expf(s[k] - m) * inv : 0.f;
         pr[k] = __float2bfloat16_rn(v);
+        if (precise) pr[L + k] = __float2bfloat16_rn(bf16_residual(v));
     }
 }
 
@@ -267,8 +280,9 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ wf,
 }
 
 // OIHW fp32 conv weight -> K-major bf16 GEMM operand: dst[o][k_off + (r*KW+s)*cin_pad + c]
+// precise mode (lo_off != 0): the row is [hi (ktot) | lo (ktot)], lo_off = ktot; `ld` = row length in elements
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
-                                                               int KH, int KW, int ktot, int k_off, int cin_pad) {
+                                                               int KH, int KW, int ld, int k_off, int cin_pad, int lo_off) {
     const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -277,7 +291,9 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
         const int rr = static_cast<int>(r % KH); r /= KH;
         const int c = static_cast<int>(r % Cin);
         const int o = static_cast<int>(r / Cin);
-        dst[static_cast<long long>(o) * ktot + k_off + (rr * KW + s) * cin_pad + c] = __float2bfloat16_rn(src[i]);
+        const long long di = static_cast<long long>(o) * ld + k_off + (rr * KW + s) * cin_pad + c;
+        dst[di] = __float2bfloat16_rn(src[i]);
+        if (lo_off) dst[di + lo_off] = __float2bfloat16_rn(bf16_residual(src[i]));
     }
 }
 
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __re
 // dst[phase][o][(a*2+b)*Cin + c]
 __global__ void __launch_bounds__(256) fold_upsample_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ d0,
                                                                    __nv_bfloat16* __restrict__ d1, __nv_bfloat16* __restrict__ d2,
-                                                                   __nv_bfloat16* __restrict__ d3, int Cout, int Cin) {
+                                                                   __nv_bfloat16* __restrict__ d3, int Cout, int Cin, int ld, int lo_off) {
     const long long total = 4LL * Cout * Cin * 4;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -302,7 +318,9 @@ __global__ void __launch_bounds__(256) fold_upsample_weight_kernel(const float* 
         for (int rr = r0; rr <= r1; ++rr)
             for (int ss = s0; ss <= s1; ++ss) acc += src[((static_cast<long long>(o) * Cin + c) * 3 + rr) * 3 + ss];
         __nv_bfloat16* d = ph == 0 ? d0 : (ph == 1 ? d1 : (ph == 2 ? d2 : d3));
-        d[static_cast<long long>(o) * (4 * Cin) + ab * Cin + c] = __float2bfloat16_rn(acc);
+        const long long di = static_cast<long long>(o) * ld + ab * Cin + c;
+        d[di] = __float2bfloat16_rn(acc);
+        if (lo_off) d[di + lo_off] = __float2bfloat16_rn(bf16_residual(acc));
     }
 }
 
@@ -313,7 +331,7 @@ __global__ void add_vec_kernel(const float* a, const float* b, float* out, int n
 
 // API boundary: NCHW fp32 (reference layout) -> bf16 NHWC channel slice of the UNet input buffer (+ optional fp32 NCHW copy).
 __global__ void __launch_bounds__(256) load_nchw_kernel(const float* __restrict__ src, int B, int C, int H, int W, __nv_bfloat16* __restrict__ in_buf,
-                                                        int in_C, int coff, float* __restrict__ copy) {
+                                                        int in_C, int coff, float* __restrict__ copy, int lo_off) {
     const long long total = static_cast<long long>(B) * C * H * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -323,7 +341,9 @@ __global__ void __launch_bounds__(256) load_nchw_kernel(const float* __restrict_
         const int c = static_cast<int>(r % C);
         const int b = static_cast<int>(r / C);
         const float v = src[i];
-        in_buf[((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c] = __float2bfloat16_rn(v);
+        const long long di = ((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c;
+        in_buf[di] = __float2bfloat16_rn(v);
+        if (lo_off) in_buf[di + lo_off] = __float2bfloat16_rn(bf16_residual(v));
         if (copy) copy[i] = v;
     }
 }
@@ -331,7 +351,7 @@ __global__ void __launch_bounds__(256) load_nchw_kernel(const float* __restrict_
 // q_sample (diffusion.py:212-219) fused with the input load: x_noisy = g * x0 + sqrt(1 - g^2) * noise, written as bf16 into the
 // UNet input buffer (channels [coff, coff+C)); g = continuous_sqrt_alpha_cumprod of the image.
 __global__ void __launch_bounds__(256) q_sample_load_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const float* __restrict__ gamma,
-                                                            int B, int C, int H, int W, __nv_bfloat16* __restrict__ in_buf, int in_C, int coff) {
+                                                            int B, int C, int H, int W, __nv_bfloat16* __restrict__ in_buf, int in_C, int coff, int lo_off) {
     const long long total = static_cast<long long>(B) * C * H * W;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -342,7 +362,9 @@ __global__ void __launch_bounds__(256) q_sample_load_kernel(const float* __restr
         const int b = static_cast<int>(r / C);
         const float g = gamma[b];
         const float v = __fadd_rn(__fmul_rn(g, x0[i]), __fmul_rn(sqrtf(__fsub_rn(1.0f, __fmul_rn(g, g))), noise[i]));
-        in_buf[((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c] = __float2bfloat16_rn(v);
+        const long long di = ((static_cast<long long>(b) * H + h) * W + w) * in_C + coff + c;
+        in_buf[di] = __float2bfloat16_rn(v);
+        if (lo_off) in_buf[di + lo_off] = __float2bfloat16_rn(bf16_residual(v));
     }
 }
 

@@ -123,6 +123,8 @@ struct GemmDesc {
     int tiles_w = 1, tiles_h = 1, tiles_b = 1, n_tiles = 1, nz = 1;
     int a_zstep = 0, b_zrows = 0;
     int z_phase = 0; long long z_off_hi = 0, z_off_lo = 0;   // nz = 4 output phases of a folded upsample conv (gemm_tcgen05.cuh)
+    int passes = 1, lo_b_col = 0, lo_a_chan[2] = {0, 0};      // precise mode: three passes over the stage table (gemm_tcgen05.cuh)
+    long long lo_out_off = 0, lo_t_off = 0;
     // epilogue
     int mode = 0, OW = 0, OH = 1, OB = 1, n_valid = 0;
     float scale = 1.f;
@@ -319,6 +321,8 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.stats = d.stats; p.stats_C = d.stats_C; p.stats_coff = d.stats_coff; p.ctl = d.ctl; p.post = d.post;
     p.t_fixed = -1;
     p.z_phase = d.z_phase; p.z_off_hi = d.z_off_hi; p.z_off_lo = d.z_off_lo;
+    p.passes = d.passes; p.lo_b_col = d.lo_b_col; p.lo_a_chan[0] = d.lo_a_chan[0]; p.lo_a_chan[1] = d.lo_a_chan[1];
+    p.lo_out_off = d.lo_out_off; p.lo_t_off = d.lo_t_off;
     if (d.stats) REQUIRE((d.w_box * d.h_box) % 32 == 0, "stats need whole warps per image");
     // fp32 output / residual through smem + TMA: one 32-row x 32-column box per epilogue warp
     p.tma_epi = (d.mode == 0 && getenv("SR3_NO_TMA_EPI") == nullptr && (d.out_f32 || d.resid)) ? 1 : 0;
@@ -363,7 +367,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
         if (ks > 1 && d.mode == 0 && d.out_f32 && d.block_n >= 32 && d.n_valid % 32 == 0) {
             int want = num_sms() / tiles;                  // CTAs per tile that still fit one wave
             if (want > ks) want = ks;
-            if (want > p.num_k / 2) want = p.num_k / 2;    // at least two stages per slice
+            if (want > p.num_k * d.passes / 2) want = p.num_k * d.passes / 2;    // at least two stages per slice
             const int units = d.mh * (d.block_n / 32) * 4; // 32x32 units of a tile: every split finalises at least one
             if (want > units) want = units;
             if (want > 1) {
@@ -443,6 +447,7 @@ int pick_block_n(int cout);
 // stages x (A box + B boxes) through TMA at a fixed ~47 B/clk, runs ceil(tiles * split / SMs) waves, and a split tile costs an extra
 // partial-tile store + reload + a grid-level handshake.  (Measured on B200: tools/gpu_splitk_sweep.py)
 void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid = false, int nz = 1) {
+    const int npass = d.passes > 1 ? d.passes : 1;
     bool tall_ok = getenv("SR3_NO_TALL") == nullptr && OW >= 8 && OH >= 16, has3 = false;
     for (const KSlab& k : d.slabs) { if (k.p != 0) tall_ok = false; if (k.dh != 0) has3 = true; }
     tall_ok = tall_ok && has3 && (OH >= 32 || Bp % 2 == 0);
@@ -495,7 +500,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
                 const long long tiles = (long long)(OW / 8) * (OH / hb) * (Bp / bb) * (cout / c.bn) * nz;
                 const long long stage_bytes = (c.mh == 2 ? 36864 : 18432) + 3ll * c.bn * 128;
                 int sp = 1;
-                const double cost = model(tiles, nstage, stage_bytes, c.mh * 128, c.bn, sp);
+                const double cost = model(tiles, nstage * npass, stage_bytes, c.mh * 128, c.bn, sp);
                 // the residual is staged through smem (8 warps x 8 KB) unless the tile is split: a 256x128 tile would be left with one stage
                 if (c.bn == 128 && has_resid && sp <= 1) continue;
                 if (cost < best) { best = cost; mh = c.mh; bn = c.bn; split = sp; }
@@ -517,7 +522,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
         const long long mt = (long long)(OW / d.w_box) * (OH / d.h_box) * (Bp / d.b_box) * nz;
         if (getenv("SR3_BLOCK_N") == nullptr && cout % 32 == 0) {
             // generic stages group up to three K slabs (one A box + one B box each)
-            const int nstage = ((int)d.slabs.size() + 2) / 3;
+            const int nstage = (((int)d.slabs.size() + 2) / 3) * npass;
             double best = 1e300;
             for (int bn = 128; bn >= 32; bn >>= 1) {
                 if (cout % bn != 0) continue;
@@ -546,7 +551,9 @@ int pick_block_n(int cout) {
     return 16;
 }
 
-void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, int stride, int b_col0) {
+// `row` = channels per pixel of the source tensor (2 * cin in precise mode: [hi | lo]); only the stride-2 view needs it
+void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, int stride, int b_col0, int row = 0) {
+    if (row == 0) row = cin;
     if (ksize == 1) {
         for (int c = 0; c < cin; c += 64) slabs.push_back({a_sel, c, 0, 0, 0, b_col0 + c});
         return;
@@ -558,7 +565,7 @@ void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, in
                 if (stride == 1) { k.dh = r - 1; k.dw = s - 1; k.p = 0; k.a_chan = c; }
                 else {   // input row 2*oh + r - 1, column 2*ow + s - 1 in the (2C, W/2, 2, H/2, B) view
                     k.dh = (r == 0) ? -1 : 0; k.p = (r == 1) ? 0 : 1;
-                    k.dw = (s == 0) ? -1 : 0; k.a_chan = ((s == 1) ? 0 : cin) + c;
+                    k.dw = (s == 0) ? -1 : 0; k.a_chan = ((s == 1) ? 0 : row) + c;
                 }
                 slabs.push_back(k);
             }
@@ -586,6 +593,7 @@ struct sr3_engine {
     sr3_unet_config cfg{};
     int B = 0, Bp = 0, dev = 0;
     int H = 0, W = 0, inner = 0, cond_c = 0, in_C = 64;
+    bool precise = false; int PW = 1;       // precise mode: every bf16 operand tensor is PW = 2 times as wide ([hi | lo] per pixel / row)
     DevAllocs mem;
     std::vector<ParamEntry> params;
     std::map<std::string, int> pindex;
@@ -679,18 +687,24 @@ struct sr3_engine {
     // conv weight packed into rows [0,Cout) of a [rows_pad][ktot] bf16 matrix at column k_off
     void conv_weight_param(const std::string& name, bf16* dst, int Cout, int Cin, int k, int ktot, int k_off, int cin_pad) {
         if (dry) return;
+        const int ld = PW * ktot, lo_off = precise ? ktot : 0;
         add_param(name, {Cout, Cin, k, k}, [=](const float* src, cudaStream_t st) {
             const long long total = 1LL * Cout * Cin * k * k;
             const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
-            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(src, dst, Cout, Cin, k, k, ktot, k_off, cin_pad);
+            pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(src, dst, Cout, Cin, k, k, ld, k_off, cin_pad, lo_off);
             CK(cudaGetLastError());
         });
     }
-    bf16* new_weight(int rows, int ktot, int block_n) {
+    bf16* new_weight(int rows, int ktot, int block_n) {      // [rows_pad][PW * ktot]: precise mode appends the low halves of every row
         if (dry) return nullptr;
         (void)block_n;
         const int rows_pad = ((rows + 127) / 128) * 128;
-        return static_cast<bf16*>(mem.alloc((size_t)rows_pad * ktot * sizeof(bf16)));
+        return static_cast<bf16*>(mem.alloc((size_t)rows_pad * PW * ktot * sizeof(bf16)));
+    }
+    // precise-mode fields of an image conv whose A sources have c0 (c1) channels and whose weight rows hold ktot (high) columns
+    void set_precise(GemmDesc& d, int c0, int c1, int ktot) {
+        if (!precise) return;
+        d.passes = 3; d.lo_a_chan[0] = c0; d.lo_a_chan[1] = c1; d.lo_b_col = ktot;
     }
     void push(Op op, int kind = 4, double flops = 0, double bytes = 0) {
         if (dry) return;
@@ -700,7 +714,7 @@ struct sr3_engine {
     // executed work of a gemm op: 2*M*N*K flops; bytes = A read once per tap set + B once + outputs
     void push_gemm(const GemmDesc& d) {
         const double M = (double)d.OW * d.OH * d.OB * (d.nz > 1 && d.a_zstep == 0 ? d.nz : 1);
-        const double K = 64.0 * d.slabs.size();
+        const double K = 64.0 * d.slabs.size() * (d.passes > 1 ? d.passes : 1);      // executed MACs (precise mode: three passes)
         const double N = d.n_valid;
         double bytes = N * K * 2;
         if (d.out_f32) bytes += M * N * 4;
@@ -719,7 +733,7 @@ struct sr3_engine {
         p.src0 = s0.p; p.st0 = s0.stats; p.C0 = s0.C;
         p.src1 = s1 ? s1->p : nullptr; p.st1 = s1 ? s1->stats : nullptr; p.C1 = s1 ? s1->C : 0;
         p.gamma = gamma; p.beta = beta; p.groups = groups; p.HW = s0.H * s0.W; p.silu = silu ? 1 : 0; p.eps = 1e-5f;
-        p.out_a = out_a; p.out_raw = out_raw;
+        p.out_a = out_a; p.out_raw = out_raw; p.precise = precise ? 1 : 0;
         const int C = p.C0 + p.C1;
         REQUIRE(C % groups == 0 && C % 4 == 0 && p.C0 % 4 == 0, "bad GroupNorm geometry C=%d groups=%d", C, groups);
         const int vpp = C / 4;
@@ -766,14 +780,17 @@ struct sr3_engine {
         bf16* raw_out = nullptr;          // also store bf16(out) (input of a following Down / Upsample conv): no separate cast pass
         bool custom_os = false; OutSpec os{};   // output addressing other than plain NHWC (phase of a folded upsample conv)
         int nz = 1, b_zrows = 0, z_phase = 0; long long z_off_hi = 0, z_off_lo = 0;   // the four phases of a folded upsample conv in ONE launch
+        int c0 = 0, c1 = 0;               // channels of the A sources (precise mode: where their low halves start)
     };
     void add_conv(const ConvArgs& c) {
         if (dry) return;
         GemmDesc d;
         d.n_a = c.n_a; d.a[0] = c.a[0]; d.a[1] = c.a[1];
         d.slabs = c.slabs;
+        REQUIRE(!precise || c.c0 > 0, "precise mode: conv without source channel counts");
+        set_precise(d, c.c0, c.c1, c.ktot);
         conv_geometry(d, c.OW, c.OH, Bp, c.cout, c.resid != nullptr, c.nz);
-        d.b_ptr = c.w; d.b_K = c.ktot; d.b_rows = (long long)c.nz * (((c.cout + 127) / 128) * 128);      // weights are padded to 128 rows (new_weight)
+        d.b_ptr = c.w; d.b_K = PW * c.ktot; d.b_rows = (long long)c.nz * (((c.cout + 127) / 128) * 128);      // weights are padded to 128 rows (new_weight)
         d.b_is_param = true;
         d.n_tiles = (c.cout + d.block_n - 1) / d.block_n; d.nz = c.nz; d.a_zstep = 0; d.b_zrows = c.b_zrows;
         d.z_phase = c.z_phase; d.z_off_hi = c.z_off_hi; d.z_off_lo = c.z_off_lo;
@@ -781,7 +798,7 @@ struct sr3_engine {
         d.bias = c.bias; d.bias2 = c.bias2; d.bias2_stride = c.bias2_stride;
         d.resid = c.resid; d.rs = nhwc_out(c.OH, c.OW, c.cout);
         d.out_f32 = c.out.p; d.os = c.custom_os ? c.os : nhwc_out(c.OH, c.OW, c.cout);
-        if (c.raw_out) { d.out_bf16 = c.raw_out; d.hs = nhwc_out(c.OH, c.OW, c.cout); }
+        if (c.raw_out) { d.out_bf16 = c.raw_out; d.hs = nhwc_out(c.OH, c.OW, PW * c.cout); d.lo_out_off = precise ? c.cout : 0; }
         d.stats = c.out.stats; d.stats_C = c.cout; d.stats_coff = 0;
         push_gemm(d);
     }
@@ -818,16 +835,16 @@ struct sr3_engine {
             }
         }
         // scratch
-        bf16* a1 = static_cast<bf16*>(role("a1", (size_t)Bp * Hh * Ww * cin * 2));
-        bf16* raw = has_res ? static_cast<bf16*>(role("raw", (size_t)Bp * Hh * Ww * cin * 2)) : nullptr;
-        bf16* a2 = static_cast<bf16*>(role("a2", (size_t)Bp * Hh * Ww * cout * 2));
+        bf16* a1 = static_cast<bf16*>(role("a1", (size_t)Bp * Hh * Ww * cin * 2 * PW));
+        bf16* raw = has_res ? static_cast<bf16*>(role("raw", (size_t)Bp * Hh * Ww * cin * 2 * PW)) : nullptr;
+        bf16* a2 = static_cast<bf16*>(role("a2", (size_t)Bp * Hh * Ww * cout * 2 * PW));
         Act h; h.C = cout; h.H = Hh; h.W = Ww; h.stats = new_stats(cout);
         h.p = static_cast<float*>(role("h", (size_t)Bp * Hh * Ww * cout * 4));
         Act y = new_act(cout, Hh, Ww, L.attn ? "" : L.name);
 
         add_prep(x, skip, g1, b1, G, true, a1, raw);
         {
-            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(a1, Bp, Hh, Ww, cin);
+            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(a1, Bp, Hh, Ww, cin * PW); c.c0 = cin;
             add_conv_slabs(c.slabs, 0, cin, 3, 1, 0);
             c.w = w1; c.ktot = 9 * cin; c.cout = cout; c.OH = Hh; c.OW = Ww;
             c.bias2 = dry ? nullptr : film + foff; c.bias2_stride = F;
@@ -836,9 +853,9 @@ struct sr3_engine {
         }
         add_prep(h, nullptr, g2, b2, G, true, a2, nullptr);
         {
-            ConvArgs c; c.n_a = has_res ? 2 : 1; c.a[0] = nhwc_src(a2, Bp, Hh, Ww, cout);
+            ConvArgs c; c.n_a = has_res ? 2 : 1; c.a[0] = nhwc_src(a2, Bp, Hh, Ww, cout * PW); c.c0 = cout;
             add_conv_slabs(c.slabs, 0, cout, 3, 1, 0);
-            if (has_res) { c.a[1] = nhwc_src(raw, Bp, Hh, Ww, cin); add_conv_slabs(c.slabs, 1, cin, 1, 1, 9 * cout); }
+            if (has_res) { c.a[1] = nhwc_src(raw, Bp, Hh, Ww, cin * PW); c.c1 = cin; add_conv_slabs(c.slabs, 1, cin, 1, 1, 9 * cout); }
             c.w = w2; c.ktot = k2; c.cout = cout; c.OH = Hh; c.OW = Ww;
             c.bias = bias_total; c.resid = has_res ? nullptr : x.p;
             c.out = y;
@@ -865,26 +882,27 @@ struct sr3_engine {
         bf16* wout = new_weight(C, C, 128);
         conv_weight_param(p + ".out.weight", wout, C, C, 1, C, 0, C);
         float* bout = f32_param(p + ".out.bias", {C});
-        bf16* n = static_cast<bf16*>(role("a1", (size_t)Bp * HW * C * 2));
-        bf16* qk = static_cast<bf16*>(role("qk", (size_t)Bp * HW * 2 * C * 2));
-        bf16* vT = static_cast<bf16*>(role("vT", (size_t)nz * C * Lt * 2));
+        bf16* n = static_cast<bf16*>(role("a1", (size_t)Bp * HW * C * 2 * PW));
+        bf16* qk = static_cast<bf16*>(role("qk", (size_t)Bp * HW * 2 * C * 2 * PW));
+        bf16* vT = static_cast<bf16*>(role("vT", (size_t)nz * C * Lt * 2 * PW));
         float* S = static_cast<float*>(role("S", (size_t)nz * Lt * Lt * 4));
-        bf16* P = static_cast<bf16*>(role("P", (size_t)nz * Lt * Lt * 2));
-        bf16* O = static_cast<bf16*>(role("O", (size_t)Bp * HW * C * 2));
+        bf16* P = static_cast<bf16*>(role("P", (size_t)nz * Lt * Lt * 2 * PW));
+        bf16* O = static_cast<bf16*>(role("O", (size_t)Bp * HW * C * 2 * PW));
         Act y = new_act(C, Hh, Ww, L.name);
         add_prep(x, nullptr, gn_w, gn_b, G, false, n, nullptr);
         if (dry) return y;
-        const bool merged_qkv = getenv("SR3_NO_MERGED_QKV") == nullptr && C % 128 == 0;     // whole 128-column tiles on either side of 2C
+        const bool merged_qkv = (getenv("SR3_NO_MERGED_QKV") == nullptr || precise) && C % 128 == 0;     // whole 128-column tiles on either side of 2C
         {   // q,k (,v) = Wqkv n : [Bp*HW tokens] x [2C (3C)]; the v columns are stored transposed as vT[z][d][token]
-            GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C);
+            GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C * PW);
             add_conv_slabs(d.slabs, 0, C, 1, 1, 0);
+            set_precise(d, C, 0, C);
             const int ncol = merged_qkv ? 3 * C : 2 * C;
-            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C; d.b_rows = ncol; d.b_is_param = true;
+            d.block_n = 128; d.b_ptr = wqkv; d.b_K = C * PW; d.b_rows = ncol; d.b_is_param = true;
             pick_image_box(Ww, Hh, d.w_box, d.h_box, d.b_box);
             d.tiles_w = Ww / d.w_box; d.tiles_h = Hh / d.h_box; d.tiles_b = Bp / d.b_box; d.n_tiles = ncol / 128;
             d.OW = Ww; d.OH = Hh; d.OB = Bp; d.n_valid = ncol;
-            d.out_bf16 = qk; d.hs = nhwc_out(Hh, Ww, 2 * C);
-            if (merged_qkv) { d.out_t = vT; d.t_col0 = 2 * C; d.t_rows = C; d.t_ld = Lt; d.t_per = per; }
+            d.out_bf16 = qk; d.hs = nhwc_out(Hh, Ww, 2 * C * PW); d.lo_out_off = precise ? 2 * C : 0;      // rows [q_hi | k_hi | q_lo | k_lo]
+            if (merged_qkv) { d.out_t = vT; d.t_col0 = 2 * C; d.t_rows = C; d.t_ld = Lt * PW; d.t_per = per; d.lo_t_off = precise ? Lt : 0; }
             push_gemm(d);
         }
         if (!merged_qkv) {   // vT[z][d][token] = Wv[d,:] . n[token,:]  (weights are the A operand, tokens the B operand)
@@ -897,15 +915,16 @@ struct sr3_engine {
             d.out_bf16 = vT; d.hs = OutSpec{(long long)C * Lt, 0, 0, Lt, 0};
             push_gemm(d);
         }
-        if (attn_fusable(Lt, C)) {
+        if (attn_fusable(Lt, C) && !precise) {
             // S = q k^T / sqrt(C), softmax over the keys of the same image, O = P v: one launch (attn_tcgen05.cuh)
             const double fl = 4.0 * nz * (double)Lt * Lt * C;
             push(make_attn_op(qk, vT, O, nz, Lt, HW, C), 5, fl, (double)nz * Lt * C * 2 * 4);
         } else {
             {   // S[z] = q k^T / sqrt(C)
-                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C, 2 * C, (long long)Lt * 2 * C);
+                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(qk, nz, Lt, 2 * C * PW, 2 * C * PW, (long long)Lt * 2 * C * PW);
                 for (int c = 0; c < C; c += 64) d.slabs.push_back({0, c, 0, 0, 0, C + c});
-                d.block_n = 128; d.b_ptr = qk; d.b_K = 2 * C; d.b_rows = (long long)Bp * HW;
+                set_precise(d, 2 * C, 0, 2 * C);
+                d.block_n = 128; d.b_ptr = qk; d.b_K = 2 * C * PW; d.b_rows = (long long)Bp * HW;
                 d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
                 d.n_tiles = Lt / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = Lt;
                 d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = Lt; d.scale = 1.0f / sqrtf((float)C);
@@ -915,23 +934,25 @@ struct sr3_engine {
             {
                 const long long rows = (long long)nz * Lt;
                 const int blocks = (int)((rows + 7) / 8);
-                push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW); }, 3, 0, (double)rows * Lt * 6.0);
-                SoftmaxParams sp{}; sp.S = S; sp.P = P; sp.rows = rows; sp.L = Lt; sp.seg = HW;
+                const int prec = precise ? 1 : 0;
+                push([=](cudaStream_t st) { launch_k(softmax_kernel, dim3(blocks), dim3(256), 0, st, (const float*)S, P, rows, Lt, HW, prec); }, 3, 0, (double)rows * Lt * 6.0);
+                SoftmaxParams sp{}; sp.S = S; sp.P = P; sp.rows = rows; sp.L = Lt; sp.seg = HW; sp.precise = prec;
                 mega_record(MOP_SOFTMAX, sp);
             }
             {   // O[z] = P v : rows = queries, N = head dim, K = keys
-                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt, Lt, (long long)Lt * Lt);
+                GemmDesc d; d.n_a = 1; d.a[0] = matrix_src(P, nz, Lt, Lt * PW, Lt * PW, (long long)Lt * Lt * PW);
                 for (int c = 0; c < Lt; c += 64) d.slabs.push_back({0, c, 0, 0, 0, c});
-                d.block_n = 128; d.b_ptr = vT; d.b_K = Lt; d.b_rows = (long long)nz * C;
+                set_precise(d, Lt, 0, Lt);
+                d.block_n = 128; d.b_ptr = vT; d.b_K = Lt * PW; d.b_rows = (long long)nz * C;
                 d.w_box = 128; d.h_box = 1; d.b_box = 1; d.tiles_w = Lt / 128; d.tiles_h = 1; d.tiles_b = 1;
                 d.n_tiles = C / 128; d.nz = nz; d.a_zstep = 1; d.b_zrows = C;
                 d.OW = Lt; d.OH = 1; d.OB = nz; d.n_valid = C;
-                d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C, 0, C, 0};
+                d.out_bf16 = O; d.hs = OutSpec{0, (long long)Lt * C * PW, 0, (long long)C * PW, 0}; d.lo_out_off = precise ? C : 0;
                 push_gemm(d);
             }
         }
         {   // out projection + bias + residual (un-normalised input)
-            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(O, Bp, Hh, Ww, C);
+            ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(O, Bp, Hh, Ww, C * PW); c.c0 = C;
             add_conv_slabs(c.slabs, 0, C, 1, 1, 0);
             c.w = wout; c.ktot = C; c.cout = C; c.OH = Hh; c.OW = Ww; c.bias = bout; c.resid = x.p; c.out = y; c.raw_out = raw_out;
             add_conv(c);
@@ -1017,24 +1038,24 @@ struct sr3_engine {
                 conv_weight_param(L.name + ".weight", w, inner, cfg.in_channel, 3, 9 * in_C, 0, in_C);
                 float* b = f32_param(L.name + ".bias", {inner});
                 x = new_act(inner, H, W, L.name);
-                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(in_buf, Bp, H, W, in_C);
+                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(in_buf, Bp, H, W, in_C * PW); c.c0 = in_C;
                 add_conv_slabs(c.slabs, 0, in_C, 3, 1, 0);
                 c.w = w; c.ktot = 9 * in_C; c.cout = inner; c.OH = H; c.OW = W; c.bias = b; c.out = x;
                 add_conv(c);
                 if (!dry) side_join = (int)ops.size();      // the FiLM biases are first read by the next block's conv1 epilogue
             } else if (L.kind == 1) {
-                bf16* xr = (fuse_cast && next_is_down) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2)) : nullptr;
+                bf16* xr = (fuse_cast && next_is_down) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2 * PW)) : nullptr;
                 x = add_res_block(L, x, nullptr, film_off, xr);
             } else {                    // Downsample: conv3x3 stride 2 on the raw stream (unet.py:68-74)
                 const int C = x.C;
                 bf16* w = new_weight(C, 9 * C, pick_block_n(C));
                 conv_weight_param(L.name + ".conv.weight", w, C, C, 3, 9 * C, 0, C);
                 float* b = f32_param(L.name + ".conv.bias", {C});
-                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * x.H * x.W * C * 2));
+                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * x.H * x.W * C * 2 * PW));
                 if (!fuse_cast) add_cast(x, raw, 1);
                 Act y = new_act(C, x.H / 2, x.W / 2, L.name);
-                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_stride2_src(raw, Bp, x.H, x.W, C);
-                add_conv_slabs(c.slabs, 0, C, 3, 2, 0);
+                ConvArgs c; c.n_a = 1; c.a[0] = nhwc_stride2_src(raw, Bp, x.H, x.W, C * PW); c.c0 = C;
+                add_conv_slabs(c.slabs, 0, C, 3, 2, 0, C * PW);
                 c.w = w; c.ktot = 9 * C; c.cout = C; c.OH = y.H; c.OW = y.W; c.bias = b; c.out = y;
                 add_conv(c);
                 x = y;
@@ -1047,7 +1068,7 @@ struct sr3_engine {
             const bool next_is_up = li + 1 < ups.size() && ups[li + 1].kind == 3;
             if (L.kind == 1) {
                 Act skip = feats.back(); feats.pop_back();
-                bf16* xr = (fuse_cast && fold_up && next_is_up) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2)) : nullptr;
+                bf16* xr = (fuse_cast && fold_up && next_is_up) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2 * PW)) : nullptr;
                 x = add_res_block(L, x, &skip, film_off, xr);
             } else if (!fold_up) {      // Upsample: nearest 2x then conv3x3 (unet.py:58-65), materialised
                 const int C = x.C;
@@ -1072,24 +1093,25 @@ struct sr3_engine {
                 bf16* wf[4];
                 if (dry) { for (int ph = 0; ph < 4; ++ph) wf[ph] = nullptr; }
                 else {
-                    bf16* wall = static_cast<bf16*>(mem.alloc((size_t)4 * rows_pad * 4 * C * sizeof(bf16)));   // [phase][rows_pad][4C]
-                    for (int ph = 0; ph < 4; ++ph) wf[ph] = wall + (size_t)ph * rows_pad * 4 * C;
+                    bf16* wall = static_cast<bf16*>(mem.alloc((size_t)4 * rows_pad * 4 * C * PW * sizeof(bf16)));   // [phase][rows_pad][PW * 4C]
+                    for (int ph = 0; ph < 4; ++ph) wf[ph] = wall + (size_t)ph * rows_pad * 4 * C * PW;
                 }
                 if (!dry) {
                     bf16* w0 = wf[0]; bf16* w1 = wf[1]; bf16* w2 = wf[2]; bf16* w3 = wf[3];
+                    const int ldw = 4 * C * PW, low = precise ? 4 * C : 0;
                     add_param(L.name + ".conv.weight", {C, C, 3, 3}, [=](const float* src, cudaStream_t st) {
                         const long long total = 4LL * C * C * 4;
-                        fold_upsample_weight_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(src, w0, w1, w2, w3, C, C);
+                        fold_upsample_weight_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(src, w0, w1, w2, w3, C, C, ldw, low);
                         CK(cudaGetLastError());
                     });
                 }
                 float* b = f32_param(L.name + ".conv.bias", {C});
-                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2));
+                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2 * PW));
                 if (!fuse_cast) add_cast(x, raw, 1);
                 Act y = new_act(C, Hl * 2, Wl * 2, L.name);
                 for (int ph = 0; ph < (merge ? 1 : 4); ++ph) {
                     const int py = ph >> 1, px = ph & 1;
-                    ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(raw, Bp, Hl, Wl, C);
+                    ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(raw, Bp, Hl, Wl, C * PW); c.c0 = C;
                     for (int a = 0; a < 2; ++a)
                         for (int bb = 0; bb < 2; ++bb)
                             for (int ch = 0; ch < C; ch += 64) {
@@ -1114,17 +1136,18 @@ struct sr3_engine {
             bf16* w = new_weight(co, 9 * C, 16);
             conv_weight_param("final_conv.block.3.weight", w, co, C, 3, 9 * C, 0, C);
             float* b = f32_param("final_conv.block.3.bias", {co});
-            bf16* a = static_cast<bf16*>(role("a1", (size_t)Bp * H * W * C * 2));
+            bf16* a = static_cast<bf16*>(role("a1", (size_t)Bp * H * W * C * 2 * PW));
             add_prep(x, nullptr, g, be, cfg.norm_groups, true, a, nullptr);
             if (!dry) {
-                GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C);
+                GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C * PW);
                 add_conv_slabs(d.slabs, 0, C, 3, 1, 0);
+                set_precise(d, C, 0, 9 * C);
                 conv_geometry(d, W, H, Bp, 16);
-                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C; d.b_rows = 128; d.n_tiles = 1; d.b_is_param = true;
+                d.block_n = 16; d.b_ptr = w; d.b_K = 9 * C * PW; d.b_rows = 128; d.n_tiles = 1; d.b_is_param = true;
                 d.mode = 1; d.OW = W; d.OH = H; d.OB = B; d.n_valid = co; d.bias = b; d.ctl = ctl_dev;
                 d.post.tab = post_tab; d.post.T = T_cap; d.post.H = H; d.post.W = W; d.post.C = co;
                 d.post.x_state = x_state; d.post.eps_out = eps_buf; d.post.mean_out = mean_buf; d.post.noise_buf = noise_buf;
-                d.post.in_buf = in_buf; d.post.in_C = in_C; d.post.in_coff = cond_c;
+                d.post.in_buf = in_buf; d.post.in_C = in_C * PW; d.post.in_coff = cond_c; d.post.in_lo_off = precise ? in_C : 0;
                 push_gemm(d);
                 // the statistics arena is cleared for the NEXT step once nobody reads it any more (every GroupNorm apply has passed
                 // the grid barrier in front of the final conv)
@@ -1146,6 +1169,8 @@ struct sr3_engine {
         REQUIRE(cfg.n_mults >= 1 && cfg.n_mults <= SR3_MAX_LEVELS, "bad n_mults");
         for (int i = 0; i < cfg.n_mults; ++i) REQUIRE((cfg.inner_channel * cfg.channel_mults[i]) % (2 * cfg.norm_groups) == 0 || (cfg.inner_channel * cfg.channel_mults[i]) % cfg.norm_groups == 0, "norm_groups must divide the channel counts");
         inner = cfg.inner_channel; H = W = cfg.image_size;
+        REQUIRE(cfg.precision == 0 || cfg.precision == 1, "precision must be 0 (bf16) or 1 (precise)");
+        precise = cfg.precision == 1; PW = precise ? 2 : 1;
         cond_c = cfg.conditional ? cfg.in_channel - cfg.channels : 0;
         Bp = (B + 1) & ~1;                         // 8x8 levels tile two images per CTA
         use_graph = getenv("SR3_NO_GRAPH") == nullptr;
@@ -1158,7 +1183,7 @@ struct sr3_engine {
         stats_arena = static_cast<double*>(mem.alloc(stats_cap * sizeof(double)));
         for (auto& kv : role_max) role_ptr[kv.first] = mem.alloc(kv.second);
         ctl_dev = static_cast<StepCtl*>(mem.alloc(sizeof(StepCtl)));
-        in_buf = static_cast<bf16*>(mem.alloc((size_t)Bp * H * W * in_C * 2));
+        in_buf = static_cast<bf16*>(mem.alloc((size_t)Bp * H * W * in_C * 2 * PW));
         const size_t img = (size_t)Bp * cfg.channels * H * W * 4;
         x_state = static_cast<float*>(mem.alloc(img)); eps_buf = static_cast<float*>(mem.alloc(img));
         mean_buf = static_cast<float*>(mem.alloc(img)); noise_buf = static_cast<float*>(mem.alloc(img));
@@ -1273,7 +1298,7 @@ struct sr3_engine {
     void load_nchw(const float* src, int C, int coff, float* copy, cudaStream_t st) {
         const long long total = 1LL * B * C * H * W;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-        load_nchw_kernel<<<blocks, 256, 0, st>>>(src, B, C, H, W, in_buf, in_C, coff, copy);
+        load_nchw_kernel<<<blocks, 256, 0, st>>>(src, B, C, H, W, in_buf, in_C * PW, coff, copy, precise ? in_C : 0);
         CK(cudaGetLastError());
     }
     size_t img_bytes() const { return (size_t)B * cfg.channels * H * W * 4; }
@@ -1300,7 +1325,7 @@ struct sr3_engine {
 extern "C" {
 
 const char* sr3_last_error(void) { return g_err.c_str(); }
-int sr3_abi_version(void) { return 1; }
+int sr3_abi_version(void) { return 2; }
 
 int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out) {
     API_BEGIN
@@ -1422,7 +1447,8 @@ int sr3_p_losses(sr3_engine* e, const float* hr, const float* sr, const float* g
     if (e->cfg.conditional) { REQUIRE(sr != nullptr, "x_in['SR'] is required by a conditional model"); e->load_nchw(sr, e->cond_c, 0, nullptr, st); }
     const long long total = 1LL * e->B * e->cfg.channels * e->H * e->W;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
-    q_sample_load_kernel<<<blocks, 256, 0, st>>>(hr, noise, gamma, e->B, e->cfg.channels, e->H, e->W, e->in_buf, e->in_C, e->cond_c);
+    q_sample_load_kernel<<<blocks, 256, 0, st>>>(hr, noise, gamma, e->B, e->cfg.channels, e->H, e->W, e->in_buf, e->in_C * e->PW, e->cond_c,
+                                                 e->precise ? e->in_C : 0);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(e->nl_buf, gamma, e->B * 4, cudaMemcpyDeviceToDevice, st));
     StepCtl& c = e->ctl; memset(&c, 0, sizeof(c));
@@ -1671,7 +1697,7 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     DevAllocs mem;
     const int ktot = ksize * ksize * Cin;
     bf16* wp = static_cast<bf16*>(mem.alloc((size_t)Cout * ktot * 2));
-    pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w_oihw, wp, Cout, Cin, ksize, ksize, ktot, 0, Cin);
+    pack_conv_weight_kernel<<<1024, 256, 0, st>>>(w_oihw, wp, Cout, Cin, ksize, ksize, ktot, 0, Cin, 0);
     CK(cudaGetLastError());
     const int OH = H / stride, OW = W / stride;
     GemmDesc d; d.n_a = 1;

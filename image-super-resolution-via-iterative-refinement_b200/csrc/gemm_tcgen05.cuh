@@ -55,6 +55,7 @@ struct PostParams {
     const float* noise_buf;   // [B,C,H,W]
     __nv_bfloat16* in_buf;    // NHWC bf16 UNet input, channel stride in_C, x_t lives at channels [in_coff, in_coff+C)
     int in_C, in_coff;
+    int in_lo_off;            // precise mode: the low halves (x - bf16(x)) live in_lo_off channels further; 0 = bf16 mode
 };
 
 // One pipeline stage of the K loop (host-built table, copied to shared memory by the kernel): up to three K slabs
@@ -126,6 +127,12 @@ struct GemmParams {
     // {2N (px, n), W, 2 (py), H, B} and plain stores add (py * z_off_hi + px * z_off_lo) elements
     int z_phase;
     long long z_off_hi, z_off_lo;
+    // Precise mode (fp32-level accuracy on the bf16 tensor cores): every operand is a pair hi = bf16(x), lo = bf16(x - hi) and a product is
+    // hi*hi + hi*lo + lo*hi (the dropped lo*lo term is ~2^-18 relative).  The K loop runs `passes` = 3 times over the SAME stage table:
+    // pass 1 reads the low weights (B column + lo_b_col), pass 2 the low activations (A channel + lo_a_chan[source]).  Low halves of
+    // bf16 outputs go lo_out_off elements (lo_t_off for the transposed store) behind the high halves.  passes = 1: plain bf16.
+    int passes, lo_b_col, lo_a_chan[2];
+    long long lo_out_off, lo_t_off;
     int t_fixed;             // >= 0: timestep of the running step (persistent step kernel: ctl->t_cur is not used there); -1: read ctl->t_cur
 };
 
@@ -234,7 +241,10 @@ __device__ __forceinline__ void final_epilogue(const GemmParams& p, const float 
         const float xn = __fadd_rn(mean, __fmul_rn(z[c], sigma));
         if (ctl.update_state) {
             q.x_state[idx] = xn;
-            q.in_buf[(static_cast<long long>(img) * plane + pix) * q.in_C + q.in_coff + c] = __float2bfloat16_rn(xn);
+            __nv_bfloat16* ib = q.in_buf + (static_cast<long long>(img) * plane + pix) * q.in_C + q.in_coff + c;
+            const __nv_bfloat16 hi = __float2bfloat16_rn(xn);
+            *ib = hi;
+            if (q.in_lo_off) ib[q.in_lo_off] = __float2bfloat16_rn(xn - __bfloat162float(hi));
         }
     }
 }
@@ -319,6 +329,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
     const int tiles_m = p.tiles_w * p.tiles_h * p.tiles_b;
     const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
     const int total_tiles = tiles_m * p.n_tiles * p.nz * ksplit;      // split index fastest: the CTAs of one output tile run together
+    const int num_kt = p.num_k * (p.passes > 1 ? p.passes : 1);       // stages per tile (precise mode: three passes over the table)
     if constexpr (!MEGA) gemm_stage_setup(p, pm, base, base_ptr, BLOCK_N, false);     // (the step kernel did this before its grid barrier)
     if constexpr (!MEGA) {
         if (warp == 1) {
@@ -374,22 +385,24 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             const int brow = n0 + z * p.b_zrows;
             const int zdw = p.z_phase ? (z & 1) : 0, zdh = p.z_phase ? (z >> 1) : 0;
             const int sp = tile % ksplit;
-            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
+            const int k0 = (num_kt * sp) / ksplit, k1 = (num_kt * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
                 mbar_wait(empty_bar(s), ph ^ 1u, 1);
                 if (elect_one_sync()) {
-                    const StageDesc& e = ktab_s[k];
+                    const int pass = k / p.num_k;
+                    const StageDesc& e = ktab_s[k - pass * p.num_k];
+                    const int a_lo = (pass == 2) ? p.lo_a_chan[e.a_sel] : 0, b_lo = (pass == 1) ? p.lo_b_col : 0;
                     const uint32_t a_dst = stage_base + s * stage_bytes;
                     const int na = e.a_multi ? e.ntaps : 1;
                     mbar_arrive_expect_tx(full_bar(s), ((p.dbg & 8) ? 0 : na * p.a_box_bytes) + ((p.dbg & 16) ? 0 : e.ntaps * B_BYTES));
                     if (!(p.dbg & 8)) {
                         for (int t = 0; t < na; ++t)
-                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &pm->a_map[e.a_sel], full_bar(s), e.tap[t].a_chan, w0 + e.tap[t].dw + zdw, e.tap[t].p,
+                            tma_load_5d(a_dst + (e.a_multi ? e.tap[t].a_off : 0), &pm->a_map[e.a_sel], full_bar(s), e.tap[t].a_chan + a_lo, w0 + e.tap[t].dw + zdw, e.tap[t].p,
                                         h0 + e.tap[t].dh + (e.a_multi ? zdh : 0), b0);     // tall halo boxes always start one row above the tile
                     }
                     if (!(p.dbg & 16)) {
                         for (int t = 0; t < e.ntaps; ++t)
-                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &pm->b_map, full_bar(s), e.tap[t].b_col, brow);
+                            tma_load_2d(a_dst + p.a_stage_bytes + t * B_BYTES, &pm->b_map, full_bar(s), e.tap[t].b_col + b_lo, brow);
                     }
                 }
                 __syncwarp();
@@ -402,7 +415,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             int filled = 0;
             for (int tile = tile_begin; tile < tile_end; ++tile) {
                 const int sp = tile % ksplit;
-                filled += (p.num_k * (sp + 1)) / ksplit - (p.num_k * sp) / ksplit;
+                filled += (num_kt * (sp + 1)) / ksplit - (num_kt * sp) / ksplit;
             }
             const int n_wait = filled < stages ? filled : stages;
             for (int i = 0; i < n_wait; ++i) {
@@ -428,12 +441,12 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                 zrow_off = (zz >> 1) * 1024;
             }
             const int sp = tile % ksplit;
-            const int k0 = (p.num_k * sp) / ksplit, k1 = (p.num_k * (sp + 1)) / ksplit;
+            const int k0 = (num_kt * sp) / ksplit, k1 = (num_kt * (sp + 1)) / ksplit;
             for (int k = k0; k < k1; ++k) {
                 mbar_wait(full_bar(s), ph, 2);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const StageDesc& e = ktab_s[k];
+                    const StageDesc& e = ktab_s[k % p.num_k];
                     if (!(p.dbg & 32)) {
                         const uint32_t a_lo = desc_lo0 + ((s * stage_bytes) >> 4);
                         const uint32_t b_lo = desc_lo0 + ((s * stage_bytes + p.a_stage_bytes) >> 4);
@@ -483,8 +496,8 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                     const int n = st_n0 + c * 32 + lane;
                     if (n < p.n_valid) {
                         double* st = p.stats + (static_cast<long long>(st_img) * p.stats_C + p.stats_coff + n) * 2;
-                        atomicAdd(st, stats_quantize(st_sum[c]));
-                        atomicAdd(st + 1, stats_quantize(st_sq[c]));
+                        red_add_f64_global(st, stats_quantize(st_sum[c]));
+                        red_add_f64_global(st + 1, stats_quantize(st_sq[c]));
                     }
                 }
             }
@@ -755,7 +768,11 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                             __nv_bfloat16* tp = p.out_t + (static_cast<long long>(img / p.t_per) * p.t_rows + (nb - p.t_col0)) * p.t_ld +
                                                 (img % p.t_per) * (p.OH * p.OW) + oh * p.OW + ow;
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) tp[static_cast<long long>(j) * p.t_ld] = __float2bfloat16_rn(f[j]);   // lanes = consecutive tokens
+                            for (int j = 0; j < 32; ++j) {                                                              // lanes = consecutive tokens
+                                const __nv_bfloat16 hi = __float2bfloat16_rn(f[j]);
+                                tp[static_cast<long long>(j) * p.t_ld] = hi;
+                                if (p.lo_t_off) tp[static_cast<long long>(j) * p.t_ld + p.lo_t_off] = __float2bfloat16_rn(f[j] - __bfloat162float(hi));
+                            }
                         }
                     } else if (row_ok && p.out_bf16) {
                         const long long ho = out_index(p.hs, z, img, oh, ow);
@@ -775,6 +792,27 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                         } else {
                             for (int j = 0; j < 32; ++j)
                                 if (nb + j < p.n_valid) p.out_bf16[ho + nb + j] = __float2bfloat16_rn(f[j]);
+                        }
+                        if (p.lo_out_off) {                       // precise mode: low halves
+                            __nv_bfloat16* lp = p.out_bf16 + ho + nb + p.lo_out_off;
+                            if (full) {
+                                uint4* o4 = reinterpret_cast<uint4*>(lp);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float r[8];
+#pragma unroll
+                                    for (int u = 0; u < 8; ++u) r[u] = f[8 * j + u] - __bfloat162float(__float2bfloat16_rn(f[8 * j + u]));
+                                    __nv_bfloat162 h0v = __floats2bfloat162_rn(r[0], r[1]), h1v = __floats2bfloat162_rn(r[2], r[3]);
+                                    __nv_bfloat162 h2v = __floats2bfloat162_rn(r[4], r[5]), h3v = __floats2bfloat162_rn(r[6], r[7]);
+                                    uint4 uu;
+                                    uu.x = *reinterpret_cast<uint32_t*>(&h0v); uu.y = *reinterpret_cast<uint32_t*>(&h1v);
+                                    uu.z = *reinterpret_cast<uint32_t*>(&h2v); uu.w = *reinterpret_cast<uint32_t*>(&h3v);
+                                    o4[j] = uu;
+                                }
+                            } else {
+                                for (int j = 0; j < 32; ++j)
+                                    if (nb + j < p.n_valid) lp[j] = __float2bfloat16_rn(f[j] - __bfloat162float(__float2bfloat16_rn(f[j])));
+                            }
                         }
                     }
                     if (p.stats && !(p.dbg & 2)) {

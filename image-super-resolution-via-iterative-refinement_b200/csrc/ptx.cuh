@@ -35,6 +35,12 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
     return t;
 }
 
+// fp64 reduction on a GLOBAL address (no return value).  Spelled in PTX because the pointer may come out of a parameter block that
+// lives in shared memory (persistent step kernel): the compiler would otherwise emit a generic-address atomic with a CAS fallback.
+__device__ __forceinline__ void red_add_f64_global(double* p, double v) {
+    asm volatile("red.global.add.f64 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "d"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");

@@ -27,7 +27,7 @@ struct MegaOp {
     long long pad;
 };
 
-struct SoftmaxParams { const float* S; __nv_bfloat16* P; long long rows; int L, seg; };
+struct SoftmaxParams { const float* S; __nv_bfloat16* P; long long rows; int L, seg, precise; };
 struct ZeroParams { float4* ptr; long long n4; };
 struct EmbedFilmParams {
     EmbedParams e;                          // ctl, nl_table, nl_buf, MLP weights, tau (unused here), inner
@@ -139,9 +139,10 @@ __device__ __forceinline__ void prep_body(const PrepParams& p, float* sm, const 
                     const float4 kk = *reinterpret_cast<const float4*>(sc + cc), ss = *reinterpret_cast<const float4*>(sh + cc);
                     float y0 = x.x * kk.x + ss.x, y1 = x.y * kk.y + ss.y, y2 = x.z * kk.z + ss.z, y3 = x.w * kk.w + ss.w;
                     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                    const long long o = (img + pix) * C + cc;
-                    *reinterpret_cast<uint2*>(p.out_a + o) = pack_bf16x4(y0, y1, y2, y3);
-                    if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = pack_bf16x4(x.x, x.y, x.z, x.w);
+                    const long long o = (img + pix) * (p.precise ? 2 * C : C) + cc;
+                    const long long lo_off = p.precise ? C : 0;
+                    store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);
+                    if (p.out_raw) store_operand4(p.out_raw, o, lo_off, x.x, x.y, x.z, x.w);
                 }
             }
             continue;
@@ -159,9 +160,10 @@ __device__ __forceinline__ void prep_body(const PrepParams& p, float* sm, const 
                 if (pp < pix1) {
                     float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
                     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                    const long long o = (img + pp) * C + c;
-                    *reinterpret_cast<uint2*>(p.out_a + o) = pack_bf16x4(y0, y1, y2, y3);
-                    if (p.out_raw) *reinterpret_cast<uint2*>(p.out_raw + o) = pack_bf16x4(x[u].x, x[u].y, x[u].z, x[u].w);
+                    const long long o = (img + pp) * (p.precise ? 2 * C : C) + c;
+                    const long long lo_off = p.precise ? C : 0;
+                    store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);
+                    if (p.out_raw) store_operand4(p.out_raw, o, lo_off, x[u].x, x[u].y, x[u].z, x[u].w);
                 }
             }
         }
@@ -175,7 +177,7 @@ __device__ __forceinline__ void softmax_body(const SoftmaxParams& p, const int c
         const int r_in = static_cast<int>(row % p.L);
         const int k0 = (r_in / p.seg) * p.seg;
         const float* s = p.S + row * p.L;
-        __nv_bfloat16* pr = p.P + row * p.L;
+        __nv_bfloat16* pr = p.P + row * (p.precise ? 2 * p.L : p.L);
         float m = -INFINITY;
         for (int k = k0 + lane; k < k0 + p.seg; k += 32) m = fmaxf(m, __ldcg(&s[k]));
 #pragma unroll
@@ -188,6 +190,7 @@ __device__ __forceinline__ void softmax_body(const SoftmaxParams& p, const int c
         for (int k = lane; k < p.L; k += 32) {
             const float v = (k >= k0 && k < k0 + p.seg) ? expf(__ldcg(&s[k]) - m) * inv : 0.f;
             pr[k] = __float2bfloat16_rn(v);
+            if (p.precise) pr[p.L + k] = __float2bfloat16_rn(bf16_residual(v));
         }
     }
 }

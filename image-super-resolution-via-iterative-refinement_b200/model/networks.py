@@ -1,6 +1,7 @@
 """Drop-in for the reference's model/networks.py:83-116 `define_G(opt)`: same `opt` schema in, an nn.Module with the
 reference's methods, attributes and state_dict layout out."""
 import logging
+import os
 
 import torch
 from torch import nn
@@ -28,7 +29,9 @@ def define_G(opt):
         norm_groups=model_opt["unet"]["norm_groups"], inner_channel=model_opt["unet"]["inner_channel"],
         channel_mults=model_opt["unet"]["channel_multiplier"], attn_res=model_opt["unet"]["attn_res"],
         res_blocks=model_opt["unet"]["res_blocks"], dropout=model_opt["unet"]["dropout"],
-        image_size=model_opt["diffusion"]["image_size"])
+        image_size=model_opt["diffusion"]["image_size"],
+        # not part of the reference's schema: optional opt['model']['unet']['precision'] in {"bf16", "fp32"} (or env SR3_PRECISION)
+        precision=(model_opt["unet"].get("precision") if hasattr(model_opt["unet"], "get") else None) or os.environ.get("SR3_PRECISION", "bf16"))
     netG = diffusion.GaussianDiffusion(
         model, image_size=model_opt["diffusion"]["image_size"], channels=model_opt["diffusion"]["channels"], loss_type="l1",
         conditional=model_opt["diffusion"]["conditional"], schedule_opt=model_opt["beta_schedule"]["train"])

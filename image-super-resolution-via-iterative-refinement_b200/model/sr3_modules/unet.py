@@ -93,8 +93,11 @@ class _Node(nn.Module):
 
 class UNet(nn.Module):
     def __init__(self, in_channel=6, out_channel=3, inner_channel=32, norm_groups=32, channel_mults=(1, 2, 4, 8, 8), attn_res=(8),
-                 res_blocks=3, dropout=0, with_noise_level_emb=True, image_size=128):
+                 res_blocks=3, dropout=0, with_noise_level_emb=True, image_size=128, precision="bf16"):
         super().__init__()
+        self.precision = "bf16"
+        self._engines = {}
+        self.set_precision(precision)
         if not with_noise_level_emb:
             raise NotImplementedError("sr3_b200 implements the noise-level conditioned UNet only")
         out_channel = out_channel if out_channel is not None else in_channel
@@ -146,6 +149,15 @@ class UNet(nn.Module):
             elif kind == "b":
                 sd[key].zero_()
 
+    def set_precision(self, precision):
+        """"bf16" (default): bf16 tensor-core operands, fp32 accumulation and residual stream -- matches the reference within 1e-2 relative.
+        "fp32": every operand is a (hi, lo) bf16 pair, three tensor-core passes per product -- matches the reference's fp32 nn.Conv2d /
+        nn.Linear arithmetic (unet.py:87) within 1e-3 relative (measured ~1e-5) at ~1/3 of the speed.  Also: env SR3_PRECISION."""
+        if precision not in _native.PRECISIONS:
+            raise ValueError("precision must be one of %s, got %r" % (sorted(_native.PRECISIONS), precision))
+        self.precision = precision
+        return self
+
     # ---- native engine management
     MAX_ENGINES = 4          # distinct (batch, device, ...) engines kept alive; least recently used ones are released
 
@@ -169,13 +181,13 @@ class UNet(nn.Module):
 
     def engine(self, batch, conditional=True, channels=3):
         dev = next(self.parameters()).device
-        key = (batch, str(dev), bool(conditional), channels)
+        key = (batch, str(dev), bool(conditional), channels, self.precision)
         eng = self._engines.pop(key, None)
         if eng is None:
             while len(self._engines) >= self.MAX_ENGINES:            # dicts keep insertion order: the first key is the least recently used
                 old = next(iter(self._engines))
                 del self._engines[old], self._engine_versions[old]
-            cfg = dict(self.arch, channels=channels, conditional=conditional)
+            cfg = dict(self.arch, channels=channels, conditional=conditional, precision=self.precision)
             eng = _native.Engine(cfg, batch, dev)
             self._engine_versions[key] = -1
             if self._schedule is not None:

@@ -34,6 +34,10 @@ typedef struct sr3_unet_config {
     int image_size;
     int channels;                      /* diffusion.channels (3) */
     int conditional;                   /* diffusion.conditional */
+    int precision;                     /* 0: bf16 operands, fp32 accumulate / stream (north_star tolerance 1e-2 rel);
+                                          1: "precise" -- every tensor-core operand is a (hi, lo) bf16 pair and each product is
+                                             hi*hi + hi*lo + lo*hi (fp32-level accuracy, north_star tolerance 1e-3 rel; ~3x the MMA work).
+                                          The reference arithmetic is fp32 nn.Conv2d / nn.Linear (unet.py:87). */
 } sr3_unet_config;
 
 typedef struct sr3_engine sr3_engine;

@@ -4,15 +4,20 @@ describes.  Everything the wrapper does with netG short of GPU compute is exerci
 set_new_noise_schedule (both phases), print_network, the Adam optimizer over our parameters, save_network / load_network with the
 reference's file naming and strict key matching, and a checkpoint written by the reference's own netG.
 
-Needs the reference checkout (build container only; the GPU box has no /root/reference -> skipped there)."""
+Needs the reference sources: /root/reference in the build container, or the verbatim copy oracle/build_ref.py puts into the
+git-ignored oracle/_ref (that copy travels to the GPU box, so the `gpu` test below -- the unmodified `DDPM.test()` / `DDPM.sample()`
+of model/model.py:60-78 driving our native sampler on a B200 -- runs there)."""
 import os
 import sys
 
 import pytest
 import torch
 
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.environ.get("SR3_REFERENCE", "/root/reference")
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model")), reason="reference checkout not present")
+if not os.path.isdir(os.path.join(REF, "model")):
+    REF = os.path.join(_ROOT, "oracle", "_ref")
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "model")), reason="reference sources not present")
 
 SCHED = {"schedule": "linear", "n_timestep": 20, "linear_start": 1e-6, "linear_end": 1e-2}
 TINY = dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2], attn_res=[16], res_blocks=1, dropout=0.0)
@@ -74,3 +79,32 @@ def test_reference_ddpm_wrapper_runs_on_our_define_g(ref_model_pkg, tmp_path):
     for k, v in ref_net.state_dict().items():
         assert torch.equal(m3.netG.state_dict()[k], v), k
     ref_net.load_state_dict(m.netG.state_dict(), strict=True)
+
+
+@pytest.mark.gpu
+def test_reference_ddpm_wrapper_samples_on_the_gpu(ref_model_pkg, tmp_path):
+    """model/model.py:60-78,98-110 unmodified: feed_data -> test(continous) -> get_current_visuals, and sample(), with netG = our define_G
+    on cuda:0; then the reference's own tensor2img (core/metrics.py:8-34) on the visuals."""
+    ref_model, ref_networks, _ = ref_model_pkg
+    import numpy as np
+    opt = make_opt("val", str(tmp_path))
+    opt["gpu_ids"] = [0]
+    torch.manual_seed(0)
+    m = ref_model.create_model(opt)
+    assert m.device.type == "cuda" and next(m.netG.parameters()).is_cuda
+    m.set_new_noise_schedule(opt["model"]["beta_schedule"]["val"], schedule_phase="val")
+    g = torch.Generator().manual_seed(3)
+    data = {"HR": torch.rand(2, 3, 32, 32, generator=g) * 2 - 1, "SR": torch.rand(2, 3, 32, 32, generator=g) * 2 - 1, "Index": torch.arange(2)}
+    m.feed_data(data)
+    m.test(continous=True)
+    vis = m.get_current_visuals()
+    n_snap = len([i for i in range(SCHED["n_timestep"]) if i % (1 | (SCHED["n_timestep"] // 10)) == 0])
+    assert vis["SR"].shape == (2 * (1 + n_snap), 3, 32, 32) and vis["SR"].device.type == "cpu" and torch.isfinite(vis["SR"]).all()
+    assert torch.equal(vis["SR"][:2], data["SR"]) and torch.equal(vis["INF"], data["SR"]) and torch.equal(vis["HR"], data["HR"])
+    m.test(continous=False)
+    last = m.get_current_visuals()["SR"]
+    assert last.shape == (3, 32, 32) and torch.isfinite(last).all()       # the reference returns ret_img[-1]: the last image only (diffusion.py:198-200)
+    # tensor2img of the reference (core/metrics.py:8-34: clamp to [-1,1] -> [0,255] uint8 HWC), restated here because core/metrics.py
+    # imports cv2, which this image does not have
+    img = ((last.clamp(-1, 1) + 1) / 2 * 255.0).round().permute(1, 2, 0).numpy().astype(np.uint8)
+    assert img.shape == (32, 32, 3) and img.dtype == np.uint8
