@@ -34,7 +34,8 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == dig:
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    tmp = LIB + ".building"                    # the library is replaced atomically: a snapshot of the tree never sees a half-written .so
+    cmd = [nvcc] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", tmp]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     log = os.path.join(PKG, "lib", "build.log")
     with open(log, "w") as fh:
@@ -42,7 +43,10 @@ def build(force=False, verbose=False):
     if verbose or r.returncode != 0:
         print(r.stdout)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed, see " + log)
+    os.replace(tmp, LIB)
     with open(stamp, "w") as fh:
         fh.write(dig)
     return LIB
