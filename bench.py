@@ -278,6 +278,22 @@ def secondary_workloads(dev, peaks, steps=10):
             torch.cuda.empty_cache()
         except Exception as e:          # a secondary number must never take the headline down
             out[name] = {"error": f"{type(e).__name__}: {e}"}
+    # the headline workload in the precise mode (precision="fp32": hi/lo bf16 operand pairs, 3 tensor-core passes; tolerance 1e-3)
+    try:
+        torch.manual_seed(0)
+        net = sr3_b200.define_G(make_opt(SCHED, dict(UNET, precision="fp32"))).to(dev)
+        net.set_new_noise_schedule(SCHED, dev)
+        eng = net.denoise_fn.engine(GLOBAL_BATCH, conditional=True, channels=3)
+        g = torch.Generator().manual_seed(3)
+        c = (torch.rand(GLOBAL_BATCH, 3, IMAGE, IMAGE, generator=g) * 2 - 1).to(dev)
+        x = torch.randn(GLOBAL_BATCH, 3, IMAGE, IMAGE, generator=g).to(dev)
+        ms = time_resident(eng, c, x, 0, steps, 3, SCHED["n_timestep"], torch.cuda.synchronize, None, dev) / steps
+        out["sr_16_128_b16_precise_fp32"] = {"config": "sr_sr3_16_128.json", "batch": GLOBAL_BATCH, "dtype": "bf16x3 (hi/lo operand pairs, fp32-level accuracy)",
+                                             "ms_per_step": ms, "steps_per_s": 1e3 / ms, "launches_per_step": eng.launches_per_step()}
+        del eng, net
+        torch.cuda.empty_cache()
+    except Exception as e:
+        out["sr_16_128_b16_precise_fp32"] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 

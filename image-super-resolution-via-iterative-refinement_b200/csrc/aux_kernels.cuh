@@ -388,4 +388,46 @@ __global__ void __launch_bounds__(256) loss_sum_kernel(const float* __restrict__
     }
 }
 
+// tensor2img of the reference (core/metrics.py:8-34) on the device: clamp to [lo, hi] -> (x - lo) / (hi - lo) -> * 255 -> round half to even
+// -> uint8, laid out HWC.  `n` images [n][C][H][W] are tiled like torchvision.utils.make_grid(nrow, padding=2, pad_value=0) when n > 1
+// (grid of ncol x nrow cells of (H+2) x (W+2) pixels plus a 2-pixel border); n == 1: plain [H][W][C].
+__global__ void __launch_bounds__(256) tensor2img_kernel(const float* __restrict__ src, unsigned char* __restrict__ dst, int n, int C, int H, int W,
+                                                         int ncol, int GH, int GW, float lo, float hi) {
+    const long long total = static_cast<long long>(GH) * GW * C;
+    const int pad = n > 1 ? 2 : 0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const int gx = static_cast<int>((i / C) % GW);
+        const int gy = static_cast<int>(i / (static_cast<long long>(C) * GW));
+        float v = 0.f;                                               // pad_value 0 (already in [0, 1] units)
+        bool inside = true;
+        int img = 0, y = gy, x = gx;
+        if (n > 1) {
+            const int cy = (gy - pad) / (H + pad), cx = (gx - pad) / (W + pad);
+            y = (gy - pad) - cy * (H + pad); x = (gx - pad) - cx * (W + pad);
+            img = cy * ncol + cx;
+            inside = gy >= pad && gx >= pad && y < H && x < W && img < n && cx < ncol;
+        }
+        if (inside) {
+            float t = src[((static_cast<long long>(img) * C + c) * H + y) * W + x];
+            t = fminf(fmaxf(t, lo), hi);
+            v = __fdiv_rn(__fsub_rn(t, lo), __fsub_rn(hi, lo));
+        }
+        dst[i] = static_cast<unsigned char>(rintf(__fmul_rn(v, 255.0f)));
+    }
+}
+
+// sum of squared differences of two uint8 images (calculate_psnr, core/metrics.py:42-50): exact in integers
+__global__ void __launch_bounds__(256) ssd_u8_kernel(const unsigned char* __restrict__ a, const unsigned char* __restrict__ b, long long n,
+                                                     unsigned long long* __restrict__ out) {
+    unsigned long long acc = 0;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int d = static_cast<int>(a[i]) - static_cast<int>(b[i]);
+        acc += static_cast<unsigned long long>(d * d);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
 }  // namespace sr3

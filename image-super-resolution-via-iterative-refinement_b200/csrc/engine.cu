@@ -1717,6 +1717,39 @@ int sr3_test_conv(const void* x, const float* w_oihw, const float* bias, float* 
     API_END
 }
 
+// core/metrics.py:8-34 tensor2img on the device (see tensor2img_kernel).  src fp32 [n][C][H][W] DEVICE, dst uint8 DEVICE [GH][GW][C] with
+// n == 1: GH = H, GW = W;  n > 1: make_grid geometry, nrow images per row: GH = rows * (H + 2) + 2, GW = ncol * (W + 2) + 2.
+int sr3_tensor2img(const float* src, unsigned char* dst, int n, int C, int H, int W, int nrow, float min_v, float max_v, void* stream) {
+    API_BEGIN
+    REQUIRE(src && dst && n >= 1 && C >= 1 && H >= 1 && W >= 1 && max_v > min_v, "bad tensor2img arguments");
+    int ncol = 1, GH = H, GW = W;
+    if (n > 1) {
+        REQUIRE(nrow >= 1, "nrow must be >= 1");
+        ncol = nrow < n ? nrow : n;                       // make_grid: xmaps = min(nrow, nmaps), ymaps = ceil(nmaps / xmaps)
+        const int rows = (n + ncol - 1) / ncol;
+        GH = rows * (H + 2) + 2; GW = ncol * (W + 2) + 2;
+    }
+    const long long total = 1LL * GH * GW * C;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 8);
+    tensor2img_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(src, dst, n, C, H, W, ncol, GH, GW, min_v, max_v);
+    CK(cudaGetLastError());
+    API_END
+}
+
+// calculate_psnr (core/metrics.py:42-50): returns the exact integer sum of squared differences of two uint8 DEVICE images through *ssd_host.
+int sr3_ssd_u8(const unsigned char* a, const unsigned char* b, int64_t n, unsigned long long* ssd_host, void* stream) {
+    API_BEGIN
+    REQUIRE(a && b && ssd_host && n >= 1, "bad arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevAllocs mem;
+    unsigned long long* d = static_cast<unsigned long long*>(mem.alloc(sizeof(unsigned long long)));
+    ssd_u8_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>(a, b, (long long)n, d);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(ssd_host, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    API_END
+}
+
 // Test hook: conv (tile kernel, statistics in its epilogue) followed by the GroupNorm(+SiLU) apply pass, i.e. one Block of the
 // reference (GN -> Swish -> conv, unet.py:80-91) seen from the GN's side: y = conv(x) + bias, a = [silu](GN(y; gamma, beta)).
 int sr3_test_conv_groupnorm(const void* x, const float* w_oihw, const float* bias, const float* gamma, const float* beta, int groups, int silu,

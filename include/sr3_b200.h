@@ -109,6 +109,15 @@ int sr3_p_sample_loop_begin(sr3_engine* e, const float* condition_x, const float
 int sr3_p_sample_steps(sr3_engine* e, int t_start, int steps, void* stream);
 int sr3_read_state(sr3_engine* e, float* x_out, void* stream);
 
+/* core/metrics.py:8-34 `tensor2img` on the device: src fp32 DEVICE [n][C][H][W] -> clamp to [min_v, max_v] -> [0, 1] -> * 255, round half
+ * to even -> uint8 DEVICE, HWC.  n == 1: dst [H][W][C].  n > 1: the images are tiled like torchvision.utils.make_grid(nrow, padding 2,
+ * pad_value 0), which is what the reference does for 4-D input: dst [rows*(H+2)+2][cols*(W+2)+2][C], cols = min(nrow, n).
+ * Saves the D2H of fp32 snapshots (model.py:98-110 get_current_visuals + sr.py): a quarter of the bytes cross PCIe. */
+int sr3_tensor2img(const float* src, unsigned char* dst_u8, int n, int C, int H, int W, int nrow, float min_v, float max_v, void* stream);
+/* core/metrics.py:42-50 `calculate_psnr`: exact integer sum of squared differences of two uint8 DEVICE images (n elements) -> *ssd_host;
+ * PSNR = 20 log10(255 / sqrt(ssd / n)) is formed by the caller in float64 as the reference does. */
+int sr3_ssd_u8(const unsigned char* a_u8, const unsigned char* b_u8, int64_t n, unsigned long long* ssd_host, void* stream);
+
 /* Introspection for tests / bench. */
 int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernel launches per reverse step: 1 with the persistent step kernel */
 int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the per-layer path (SR3_NO_MEGA=1 / sr3_engine_profile_step) */

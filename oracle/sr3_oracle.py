@@ -452,3 +452,50 @@ def init_state_dict(cfg: UNetConfig, seed: int = 0, orthogonal: bool = False, dt
             elif kind in ("conv_b", "lin_b"):
                 sd[name].zero_()
     return {k: v.to(dtype) for k, v in sd.items()}
+
+
+# --------------------------------------------------------------------------------------
+# exit of the sampling path: core/metrics.py (tensor2img, calculate_psnr)
+# --------------------------------------------------------------------------------------
+def make_grid_np(t: np.ndarray, nrow: int, padding: int = 2) -> np.ndarray:
+    """torchvision.utils.make_grid(tensor, nrow, padding=2, normalize=False, pad_value=0) as the reference calls it
+    (core/metrics.py:20-21): [B,C,H,W] -> [C', rows*(H+2)+2, cols*(W+2)+2]; single-channel images are repeated to 3 channels."""
+    if t.shape[1] == 1:
+        t = np.repeat(t, 3, axis=1)
+    n, c, h, w = t.shape
+    xmaps = min(nrow, n)
+    ymaps = int(math.ceil(float(n) / xmaps))
+    hh, ww = h + padding, w + padding
+    grid = np.zeros((c, hh * ymaps + padding, ww * xmaps + padding), dtype=t.dtype)
+    k = 0
+    for y in range(ymaps):
+        for x in range(xmaps):
+            if k >= n:
+                break
+            grid[:, y * hh + padding:y * hh + padding + h, x * ww + padding:x * ww + padding + w] = t[k]
+            k += 1
+    return grid
+
+
+def tensor2img(tensor: Tensor, min_max=(-1, 1)) -> np.ndarray:
+    """core/metrics.py:8-34 (out_type uint8)."""
+    t = tensor.squeeze().float().cpu().clamp(*min_max)
+    t = (t - min_max[0]) / (min_max[1] - min_max[0])
+    if t.dim() == 4:
+        img = np.transpose(make_grid_np(t.numpy(), int(math.sqrt(len(t)))), (1, 2, 0))
+    elif t.dim() == 3:
+        img = np.transpose(t.numpy(), (1, 2, 0))
+    elif t.dim() == 2:
+        img = t.numpy()
+    else:
+        raise TypeError("Only support 4D, 3D and 2D tensor")
+    return (img * 255.0).round().astype(np.uint8)
+
+
+def calculate_psnr(img1: np.ndarray, img2: np.ndarray) -> float:
+    """core/metrics.py:42-50."""
+    a, b = img1.astype(np.float64), img2.astype(np.float64)
+    mse = np.mean((a - b) ** 2)
+    if mse == 0:
+        return float("inf")
+    return 20 * math.log10(255.0 / math.sqrt(mse))
