@@ -187,6 +187,21 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
 }
 template <int BN, int MH>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (p.ksplit > 1) CK(cudaStreamIsCapturing(st, &cap));
+    if (p.ksplit > 1 && cap == cudaStreamCaptureStatusNone && getenv("SR3_NO_COOP") == nullptr) {
+        // split-K CTAs wait for their partners inside the kernel: launch cooperatively so that the runtime guarantees co-residency
+        // (or fails the launch) even when another stream / engine / library kernel holds SMs.  No PDL overlap for these launches.
+        // (Launches being captured into the per-layer step graph keep the plain form: that graph runs alone on its stream.)
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeCooperative;
+        attr[0].val.cooperative = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, MH>, p));
+        return;
+    }
     launch_k(gemm_tile_kernel<BN, MH>, grid, dim3(GEMM_THREADS), (size_t)smem, st, p);
 }
 void init_gemm_attrs() {

@@ -49,8 +49,9 @@ int sr3_abi_version(void);
 
 /* UNet.__init__ (model/sr3_modules/unet.py:161-233) + GaussianDiffusion.__init__ (diffusion.py:64-82):
  * builds the layer plan, allocates activations / packed weights on `device` for a fixed batch size.
- * Threading: calls on one engine must be serialised by the caller; engines on the SAME device must not execute concurrently
- * on different streams unless SR3_NO_KSPLIT=1 (the split-K layers wait for co-resident partner CTAs). */
+ * Threading: calls on one engine must be serialised by the caller.  Kernels that wait for partner CTAs (the persistent step kernel's grid
+ * barriers, split-K tile launches of the per-layer path) are launched cooperatively, so engines driven concurrently from different
+ * streams of one device serialise instead of deadlocking. */
 int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out);
 void sr3_engine_destroy(sr3_engine* e);
 
