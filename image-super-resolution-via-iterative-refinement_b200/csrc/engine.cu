@@ -326,6 +326,11 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
     p.b_taps = b_taps; p.a_half_off = d.a_half_off;
     p.tiles_w = d.tiles_w; p.tiles_h = d.tiles_h; p.tiles_b = d.tiles_b;
     p.w_box = d.w_box; p.h_box = d.h_box; p.b_box = d.b_box;
+    {
+        auto lg = [](int v) { int l = 0; while ((1 << l) < v) ++l; return l; };
+        REQUIRE((d.w_box & (d.w_box - 1)) == 0 && (d.h_box & (d.h_box - 1)) == 0, "tile box %dx%d must be powers of two", d.w_box, d.h_box);
+        p.w_shift = lg(d.w_box); p.h_shift = lg(d.h_box);
+    }
     p.a_zstep = d.a_zstep; p.b_zrows = d.b_zrows;
     p.dbg = getenv("SR3_DBG") ? atoi(getenv("SR3_DBG")) : 0;
     p.n_tiles = d.n_tiles; p.nz = d.nz;

@@ -98,7 +98,8 @@ struct GemmParams {
     long long pf_bytes;      // first-touch HBM reads on the critical path of every pipeline stage of that launch)
     int dbg;                 // SR3_DBG bit mask (timing experiments only): 1 skip epilogue body, 2 skip stats, 4 skip out store,
                              // 8 skip A loads, 16 skip B loads, 32 skip MMAs
-    int w_box, h_box, b_box; // pixel patch of one tile: w_box * h_box * b_box == MH * 128
+    int w_box, h_box, b_box; // pixel patch of one tile: w_box * h_box * b_box == MH * 128 (all powers of two)
+    int w_shift, h_shift;    // log2(w_box), log2(h_box): the epilogue splits a tile row into (w, h, image) with shifts, not divisions
     int a_zstep, b_zrows;
     int stages;
     // epilogue
@@ -515,9 +516,9 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             auto item_geom = [&](int item, int qq, int& half, int& ch, int& sw, int& sh, int& c4) {
                 half = item / NCH; ch = item % NCH;
                 const int r0 = half * 128 + qq * 32;
-                sw = r0 % p.w_box;
-                sh = (r0 / p.w_box) % p.h_box;
-                const int sb = r0 / (p.w_box * p.h_box);
+                sw = r0 & (p.w_box - 1);
+                sh = (r0 >> p.w_shift) & (p.h_box - 1);
+                const int sb = r0 >> (p.w_shift + p.h_shift);
                 c4 = p.epi_c4_is_z ? z : (b0 + sb);
             };
             auto request_resid = [&](int item) {                   // lane 0 only
@@ -540,7 +541,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                     float bv = 0.f;
                     if (item < NITEMS) {
                         const int half = item / NCH, ch = item % NCH;
-                        const int bb = (half * 128 + q * 32) / (p.w_box * p.h_box);
+                        const int bb = (half * 128 + q * 32) >> (p.w_shift + p.h_shift);
                         const int img = b0 + bb;
                         const int n = n0 + ch * 32 + lane;
                         if (n < p.n_valid) {
@@ -608,9 +609,9 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                 item_geom(item, qq, half, ch, sw, sh, c4);
                 const bool last_item = !from_ws && (item + 2 >= NITEMS);
                 const int row = half * 128 + qq * 32 + lane;
-                const int w = row % p.w_box;
-                const int h = (row / p.w_box) % p.h_box;
-                const int bb = row / (p.w_box * p.h_box);
+                const int w = row & (p.w_box - 1);
+                const int h = (row >> p.w_shift) & (p.h_box - 1);
+                const int bb = row >> (p.w_shift + p.h_shift);
                 const int ow = w0 + w, oh = h0 + h, img = b0 + bb;
                 const bool row_ok = (ow < p.OW) && (oh < p.OH) && (img < p.OB);
                 if (p.stats && !(p.dbg & 2) && !to_ws) {
@@ -641,7 +642,7 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                         if (n < p.n_valid) {
                             if (p.bias) bv += __ldg(&p.bias[n]);
                             if (p.bias2) {
-                                const int img0 = b0 + (half * 128 + qq * 32) / (p.w_box * p.h_box);
+                                const int img0 = b0 + ((half * 128 + qq * 32) >> (p.w_shift + p.h_shift));
                                 bv += __ldcg(&p.bias2[static_cast<long long>(img0 < p.OB ? img0 : 0) * p.bias2_stride + n]);
                             }
                         }
@@ -827,16 +828,24 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
                             // mean), the shift is put back in fp64:  sum x = a + n s,  sum x^2 = q + 2 s a + n s^2
                             const float sft = *reinterpret_cast<const float*>(colp + (cq4 << 4));
                             float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+                            if (okm == 0xffffffffu) {            // (warp-uniform) the usual case: no padded pixel / image in this chunk
 #pragma unroll
-                            for (int r = 0; r < 32; r += 2) {
-                                float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4)) - sft;
-                                float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4)) - sft;
-                                if (okm != 0xffffffffu) {
+                                for (int r = 0; r < 32; r += 2) {
+                                    const float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4)) - sft;
+                                    const float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4)) - sft;
+                                    a0 += x0; q0 = fmaf(x0, x0, q0);
+                                    a1 += x1; q1 = fmaf(x1, x1, q1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int r = 0; r < 32; r += 2) {
+                                    float x0 = *reinterpret_cast<const float*>(colp + r * 128 + ((cq4 ^ (r & 7)) << 4)) - sft;
+                                    float x1 = *reinterpret_cast<const float*>(colp + (r + 1) * 128 + ((cq4 ^ ((r + 1) & 7)) << 4)) - sft;
                                     if (!((okm >> r) & 1u)) x0 = 0.f;
                                     if (!((okm >> (r + 1)) & 1u)) x1 = 0.f;
+                                    a0 += x0; q0 = fmaf(x0, x0, q0);
+                                    a1 += x1; q1 = fmaf(x1, x1, q1);
                                 }
-                                a0 += x0; q0 = fmaf(x0, x0, q0);
-                                a1 += x1; q1 = fmaf(x1, x1, q1);
                             }
                             const double n_ok = static_cast<double>(__popc(okm)), ds = static_cast<double>(sft);
                             const double da = static_cast<double>(a0 + a1), dq = static_cast<double>(q0 + q1);
