@@ -411,7 +411,7 @@ def main():
         return
 
     # ---------------- roofline of the dominant kernel.  With the persistent step kernel the step IS one launch: its average duration
-    # is the event-timed region / K.  (Per-layer path, SR3_NO_MEGA=1: the summed event durations of the tile-kernel launches.)
+    # is the event-timed region / K.  (Per-layer path, the default: the summed event durations of the tile-kernel launches.)
     peaks = measured_peaks()
     alg_flops_step = algorithmic_flops_per_image() * per
     by_op = None

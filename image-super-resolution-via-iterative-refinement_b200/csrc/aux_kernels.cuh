@@ -44,23 +44,48 @@ struct PrepParams {
 };
 
 // Per-(image, channel) scale / shift of a GroupNorm from the fp64 channel sums: y = x * sc[c] + sh[c].
-// sc / sh: [C] floats in shared memory; scratch gm / gr: [groups] each.  Ends with a __syncthreads().
+// sc / sh: [C] floats each, CONTIGUOUS ([2C] floats = [C] doubles of scratch) in shared memory; gm / gr: [groups] each.
+// All channel sums are fetched in ONE parallel round trip (a thread per channel), then reduced per group from shared memory.
+// Ends with a __syncthreads().
 __device__ __forceinline__ void groupnorm_scale_shift(const PrepParams& p, int b, float* sc, float* sh, float* gm, float* gr) {
     const int C = p.C0 + p.C1;
     const int gs = C / p.groups;
+    // pass 1: the (sum, sumsq) pairs, as fp64, into registers -> group partials via shared memory.  The [2C]-float sc/sh area holds C
+    // doubles: first all the sums, then (after the group means are known) all the sums of squares.
+    double* scratch = reinterpret_cast<double*>(sc);
+    constexpr int MAXC = 10;                             // channels per thread: C <= 10 * blockDim.x (3072 channels at 320 threads)
+    double2 mine[MAXC];
+    int nmine = 0;
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k) {
+        const int c = threadIdx.x + k * blockDim.x;
+        if (c >= C) break;
+        mine[k] = (c < p.C0) ? __ldcg(reinterpret_cast<const double2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
+                                     : __ldcg(reinterpret_cast<const double2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
+        nmine = k + 1;
+    }
+    const double inv = 1.0 / (static_cast<double>(gs) * static_cast<double>(p.HW));
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k)
+        if (k < nmine) scratch[threadIdx.x + k * blockDim.x] = mine[k].x;
+    __syncthreads();
+    double gmean = 0.0;
+    for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {        // groups <= blockDim.x: one iteration
+        double s = 0.0;
+        for (int j = 0; j < gs; ++j) s += scratch[g * gs + j];
+        gmean = s * inv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < MAXC; ++k)
+        if (k < nmine) scratch[threadIdx.x + k * blockDim.x] = mine[k].y;
+    __syncthreads();
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
-        double s = 0.0, q = 0.0;
-        for (int j = 0; j < gs; ++j) {
-            const int c = g * gs + j;
-            const double2 st = (c < p.C0) ? __ldcg(reinterpret_cast<const double2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
-                                          : __ldcg(reinterpret_cast<const double2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
-            s += st.x; q += st.y;
-        }
-        const double inv = 1.0 / (static_cast<double>(gs) * static_cast<double>(p.HW));
-        const double mean = s * inv;
-        double var = q * inv - mean * mean;                 // fp64: no cancellation problem for |mean| >> std
+        double q = 0.0;
+        for (int j = 0; j < gs; ++j) q += scratch[g * gs + j];
+        double var = q * inv - gmean * gmean;               // fp64: no cancellation problem for |mean| >> std
         if (var < 0.0) var = 0.0;
-        gm[g] = static_cast<float>(mean);
+        gm[g] = static_cast<float>(gmean);
         gr[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(p.eps)));
     }
     __syncthreads();

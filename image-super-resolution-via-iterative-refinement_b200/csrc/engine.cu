@@ -1235,7 +1235,10 @@ struct sr3_engine {
 
     // ---- persistent step kernel: serialise the recorded ops (parameter blocks 128-byte aligned) and upload them
     void build_mega() {
-        use_mega = getenv("SR3_NO_MEGA") == nullptr && getenv("SR3_NO_FUSE_CAST") == nullptr && getenv("SR3_NO_FOLD_UP") == nullptr;
+        // Off by default: measured on the B200 (profiles/r02_step_kernel.md) the grid barrier + per-op fill / drain costs as much as a
+        // launch inside a CUDA graph, and the 320-thread GroupNorm apply runs at half the bandwidth of the stand-alone kernel.
+        // SR3_MEGA=1 selects it (bit-identical results).
+        use_mega = getenv("SR3_MEGA") != nullptr && atoi(getenv("SR3_MEGA")) != 0 && getenv("SR3_NO_FUSE_CAST") == nullptr && getenv("SR3_NO_FOLD_UP") == nullptr;
         if (!use_mega) return;
         std::vector<MegaOp> host_ops;
         std::vector<uint8_t> blob;
@@ -1601,7 +1604,7 @@ int sr3_engine_uses_step_kernel(const sr3_engine* e) { return (e && e->use_mega)
 int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, int* n_ops, void* stream) {
     API_BEGIN
     REQUIRE(e && types && us && n_ops, "null argument");
-    REQUIRE(e->use_mega, "this engine runs the per-layer path (SR3_NO_MEGA), there is no step kernel to profile");
+    REQUIRE(e->use_mega, "this engine runs the per-layer path (set SR3_MEGA=1 for the step kernel), there is nothing to profile here");
     const int n = (int)e->mega_types.size();
     REQUIRE(cap >= n, "profile buffers too small (%d ops)", n);
     CK(cudaSetDevice(e->dev));

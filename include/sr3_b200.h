@@ -121,9 +121,9 @@ int sr3_ssd_u8(const unsigned char* a_u8, const unsigned char* b_u8, int64_t n, 
 
 /* Introspection for tests / bench. */
 int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernel launches per reverse step: 1 with the persistent step kernel */
-int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the per-layer path (SR3_NO_MEGA=1 / sr3_engine_profile_step) */
+int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the per-layer path (the default; also what sr3_engine_profile_step times) */
 /* 1 when one reverse step (reference p_sample: diffusion.py:151-174, UNet.forward unet.py:235-259) runs as ONE persistent
- * cooperative launch (csrc/step_megakernel.cuh), 0 when it runs as a CUDA graph of per-layer launches (SR3_NO_MEGA=1). */
+ * cooperative launch (csrc/step_megakernel.cuh), 0 when it runs as a CUDA graph of per-layer launches (the default; SR3_MEGA=1 selects the step kernel). */
 int sr3_engine_uses_step_kernel(const sr3_engine* e);
 /* Per-op device time (us) of the most recent step-kernel launch: globaltimer stamps taken by CTA 0 after each grid barrier.
  * types: 0 tensor-core tile loop, 1 GroupNorm apply, 2 fused attention, 3 row softmax, 4 embedding + FiLM, 5 statistics clear. */

@@ -109,7 +109,7 @@ def test_conv_dgrad_is_the_forward_kernel_on_mirrored_weights(B, H, W, Cin, Cout
 
 
 @pytest.mark.parametrize("B,H,W,Cin,Cout,groups,ratio", [(2, 32, 32, 64, 128, 32, 30.0), (2, 16, 16, 128, 64, 16, 30.0), (1, 64, 64, 64, 64, 32, 100.0),
-                                                         (3, 8, 8, 64, 256, 32, 0.0)])
+                                                         (4, 8, 8, 64, 256, 32, 0.0)])
 def test_groupnorm_is_cancellation_safe(B, H, W, Cin, Cout, groups, ratio):
     """GroupNorm statistics (reference nn.GroupNorm(groups, dim), eps 1e-5, unet.py:84,119) for activations whose |mean| / std is ~30-100
     and with non-trivial affine weights: the conv epilogue accumulates shifted sums, the totals are fp64 -- a one-pass fp32

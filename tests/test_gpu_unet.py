@@ -210,16 +210,16 @@ def test_sharded_super_resolution_single_rank(golden):
 @pytest.mark.parametrize("batch", [2, 3])
 def test_step_kernel_matches_per_layer_path_bit_for_bit(golden, batch, monkeypatch):
     """One reverse step as ONE persistent cooperative launch (csrc/step_megakernel.cuh) against the same plan run as a CUDA graph of
-    per-layer launches (SR3_NO_MEGA=1): identical arithmetic, identical bits -- for eps and for a seeded 10-step loop."""
+    per-layer launches (the default; SR3_MEGA=1 selects the step kernel): identical arithmetic, identical bits -- for eps and for a seeded 10-step loop."""
     g = golden["tiny_diffusion"]
     c = g["cond"][:batch] if batch <= g["cond"].shape[0] else torch.cat([g["cond"], g["cond"][:1]], 0)
     xT = g["x_T"][:batch] if batch <= g["x_T"].shape[0] else torch.cat([g["x_T"], g["x_T"][:1]], 0)
     outs = {}
     for mode in ("mega", "layers"):
-        if mode == "layers":
-            monkeypatch.setenv("SR3_NO_MEGA", "1")
+        if mode == "mega":
+            monkeypatch.setenv("SR3_MEGA", "1")
         else:
-            monkeypatch.delenv("SR3_NO_MEGA", raising=False)
+            monkeypatch.delenv("SR3_MEGA", raising=False)
         net = build(TINY_UNET, 32, 0, sched=g["sched"])
         eng = net.denoise_fn.engine(batch)
         assert eng.uses_step_kernel() == (mode == "mega")
@@ -230,7 +230,7 @@ def test_step_kernel_matches_per_layer_path_bit_for_bit(golden, batch, monkeypat
         loop = net.super_resolution(c.cuda(), continous=True, x_T=xT.cuda(), seed=5)
         outs[mode] = (eps.cpu(), loop.cpu())
         del eng, net
-    monkeypatch.delenv("SR3_NO_MEGA", raising=False)
+    monkeypatch.delenv("SR3_MEGA", raising=False)
     assert torch.equal(outs["mega"][0], outs["layers"][0])
     assert torch.equal(outs["mega"][1], outs["layers"][1])
 

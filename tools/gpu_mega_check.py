@@ -17,9 +17,9 @@ dev = torch.device("cuda", 0)
 
 def build(unet, size, B, mega):
     if mega:
-        os.environ.pop("SR3_NO_MEGA", None)
+        os.environ["SR3_MEGA"] = "1"
     else:
-        os.environ["SR3_NO_MEGA"] = "1"
+        os.environ.pop("SR3_MEGA", None)
     opt = {"phase": "val", "gpu_ids": [0], "distributed": False,
            "model": {"which_model_G": "sr3", "finetune_norm": False, "unet": dict(unet), "beta_schedule": {"train": SCHED, "val": SCHED},
                      "diffusion": {"image_size": size, "channels": 3, "conditional": True}}}
@@ -27,7 +27,7 @@ def build(unet, size, B, mega):
     net = sr3_b200.define_G(opt).to(dev)
     net.set_new_noise_schedule(SCHED, dev)
     eng = net.denoise_fn.engine(B, conditional=True, channels=3)
-    os.environ.pop("SR3_NO_MEGA", None)
+    os.environ.pop("SR3_MEGA", None)
     return net, eng
 
 
