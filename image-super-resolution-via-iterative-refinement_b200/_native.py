@@ -52,7 +52,7 @@ _SIGS = {
     "sr3_engine_num_launches_per_step": (c_int, [c_void_p]),
     "sr3_engine_num_ops_per_step": (c_int, [c_void_p]),
     "sr3_engine_uses_step_kernel": (c_int, [c_void_p]),
-    "sr3_engine_step_kernel_profile": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_double), POINTER(c_int), c_void_p]),
+    "sr3_engine_step_kernel_profile": (c_int, [c_void_p, c_int, POINTER(c_int), POINTER(c_double), POINTER(c_double), POINTER(c_int), c_void_p]),
     "sr3_engine_workspace_bytes": (c_int64, [c_void_p]),
     "sr3_engine_read_activation": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, POINTER(c_int64), POINTER(c_int), c_void_p]),
     "sr3_bench_conv": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_float)]),
@@ -283,13 +283,16 @@ class Engine:
 
     STEP_OP_NAMES = {0: "gemm_tile", 1: "groupnorm_apply", 2: "attention", 3: "softmax", 4: "embed_film", 5: "stats_clear"}
 
-    def step_kernel_profile(self):
-        """[(op type, microseconds)] of the most recent persistent-step-kernel launch (device globaltimer stamps)."""
+    def step_kernel_profile(self, phases=False):
+        """[(op type, microseconds)] of the most recent persistent-step-kernel launch (device globaltimer stamps of CTA 0);
+        phases=True: [(op type, us, (set-up, barrier wait, body, end fence))]."""
         cap = 4096
-        types, us = (c_int * cap)(), (c_double * cap)()
+        types, us, ph = (c_int * cap)(), (c_double * cap)(), (c_double * (4 * cap))()
         n = c_int()
         with torch.cuda.device(self.device):
-            _check(lib().sr3_engine_step_kernel_profile(self._h, cap, types, us, ctypes.byref(n), _stream()))
+            _check(lib().sr3_engine_step_kernel_profile(self._h, cap, types, us, ph, ctypes.byref(n), _stream()))
+        if phases:
+            return [(types[i], us[i], tuple(ph[4 * i + k] for k in range(4))) for i in range(n.value)]
         return [(types[i], us[i]) for i in range(n.value)]
 
     def workspace_bytes(self):

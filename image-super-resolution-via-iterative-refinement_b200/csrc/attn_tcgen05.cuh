@@ -231,10 +231,7 @@ __device__ __forceinline__ void attn_unit(const AttnParams& p, const AttnParams*
             }
         }
     }
-    if constexpr (MEGA) {
-        __threadfence();
-        fence_proxy_async_all();
-    }
+    if constexpr (MEGA) fence_proxy_async_all();      // the next unit's TMA loads overwrite shared memory this unit wrote generically
     tc_fence_before();
     __syncthreads();
     if constexpr (!MEGA) {

@@ -1266,7 +1266,7 @@ struct sr3_engine {
         mega_ops_dev = static_cast<MegaOp*>(mem.alloc(host_ops.size() * sizeof(MegaOp), false));
         mega_blob = static_cast<uint8_t*>(mem.alloc(blob.size(), false));
         mega_bar = static_cast<unsigned long long*>(mem.alloc(128));
-        mega_prof = static_cast<unsigned long long*>(mem.alloc((host_ops.size() + 1) * sizeof(unsigned long long)));
+        mega_prof = static_cast<unsigned long long*>(mem.alloc((host_ops.size() + 1) * 4 * sizeof(unsigned long long)));
         REQUIRE((reinterpret_cast<uintptr_t>(mega_blob) & 127) == 0, "blob not 128B aligned");
         CK(cudaMemcpy(mega_ops_dev, host_ops.data(), host_ops.size() * sizeof(MegaOp), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(mega_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
@@ -1601,7 +1601,7 @@ int sr3_engine_profile_step(sr3_engine* e, int t, int reps, int cap, int* kinds,
 int sr3_engine_uses_step_kernel(const sr3_engine* e) { return (e && e->use_mega) ? 1 : 0; }
 
 // Per-op device time of the most recent step-kernel launch (globaltimer stamps taken by CTA 0 after each grid barrier).
-int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, int* n_ops, void* stream) {
+int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, double* phases, int* n_ops, void* stream) {
     API_BEGIN
     REQUIRE(e && types && us && n_ops, "null argument");
     REQUIRE(e->use_mega, "this engine runs the per-layer path (set SR3_MEGA=1 for the step kernel), there is nothing to profile here");
@@ -1609,9 +1609,18 @@ int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* u
     REQUIRE(cap >= n, "profile buffers too small (%d ops)", n);
     CK(cudaSetDevice(e->dev));
     CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
-    std::vector<unsigned long long> ts(n + 1);
+    std::vector<unsigned long long> ts((size_t)(n + 1) * 4);
     CK(cudaMemcpy(ts.data(), e->mega_prof, ts.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    for (int i = 0; i < n; ++i) { types[i] = e->mega_types[i]; us[i] = (double)(ts[i + 1] - ts[i]) * 1e-3; }
+    for (int i = 0; i < n; ++i) {
+        types[i] = e->mega_types[i];
+        us[i] = (double)(ts[4 * (i + 1)] - ts[4 * i]) * 1e-3;
+        if (phases) {      // [set-up (arrive + parameter / stage-table copy), barrier wait, body, end-of-op fence]
+            phases[4 * i + 0] = (double)(ts[4 * i + 1] - ts[4 * i]) * 1e-3;
+            phases[4 * i + 1] = (double)(ts[4 * i + 2] - ts[4 * i + 1]) * 1e-3;
+            phases[4 * i + 2] = (double)(ts[4 * i + 3] - ts[4 * i + 2]) * 1e-3;
+            phases[4 * i + 3] = (double)(ts[4 * (i + 1)] - ts[4 * i + 3]) * 1e-3;
+        }
+    }
     *n_ops = n;
     API_END
 }

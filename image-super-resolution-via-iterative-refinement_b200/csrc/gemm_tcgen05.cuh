@@ -878,12 +878,8 @@ __device__ __forceinline__ void gemm_tile_body(const GemmParams& p, const GemmPa
             if (use_out_tma && out_pending && lane == 0) tma_store_wait_read<0>();     // smem must outlive the reads of the last bulk stores
         }
     }
-    if constexpr (MEGA) {
-        __threadfence();
-        fence_proxy_async_all();      // st.global results are read through TMA by the next op; its TMA loads also overwrite smem we touched
-    }
     tc_fence_before();
-    __syncthreads();
+    if constexpr (!MEGA) __syncthreads();      // (the step kernel fences and synchronises after every op itself)
     if constexpr (!MEGA) {
         if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
     }

@@ -41,7 +41,8 @@ struct MegaParams {
     int n_ops;
     const uint8_t* blob;
     unsigned long long* bar;                // grid-barrier counter (monotonic)
-    unsigned long long* prof;               // [n_ops + 1] globaltimer stamps of CTA 0 (nullptr: off)
+    unsigned long long* prof;               // [n_ops + 1][4] globaltimer stamps of CTA 0 (nullptr: off): op start (previous op done),
+                                            // barrier arrived + set-up done, barrier passed, body done
     StepCtl* ctl;
 };
 
@@ -93,7 +94,7 @@ struct GridBarrier {
 // Same arithmetic as prep_kernel (aux_kernels.cuh) for the 320-thread CTAs of the step kernel: a CTA owns a contiguous range of
 // (image, pixel block) items; scale / shift are rebuilt when the image changes.  Loads are L2-coherent (.cg): the data was produced
 // earlier in the same launch.
-__device__ __forceinline__ void prep_body(const PrepParams& p, float* sm, const int cta, const int ncta) {
+__device__ __noinline__ void prep_body(const PrepParams& p, float* sm, const int cta, const int ncta) {
     const int C = p.C0 + p.C1;
     float* sc = sm;
     float* sh = sm + C;
@@ -106,30 +107,28 @@ __device__ __forceinline__ void prep_body(const PrepParams& p, float* sm, const 
     const bool active = wide || static_cast<int>(threadIdx.x) < vpp * kpix;
     const int c = wide ? 0 : (threadIdx.x % vpp) << 2;
     const int lp = wide ? 0 : threadIdx.x / vpp;
-    const long long items = static_cast<long long>(p.B) * p.items_per_image;
-    const long long i0 = items * cta / ncta, i1 = items * (cta + 1) / ncta;
+    // this CTA's share: a contiguous range of the B x HW pixels (whole multiples of the kpix pixels a pass of the block covers)
+    const long long total = static_cast<long long>(p.B) * p.HW;
+    const long long units = (total + kpix - 1) / kpix;
+    const long long g0 = (units * cta / ncta) * kpix;
+    long long g1 = (units * (cta + 1) / ncta) * kpix;
+    if (g1 > total) g1 = total;
     const bool from0 = c < p.C0;
     const float* src = from0 ? p.src0 + c : p.src1 + (c - p.C0);
     const int cs = from0 ? p.C0 : p.C1;
-    int cur_b = -1;
     float k4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {0.f, 0.f, 0.f, 0.f};
-    constexpr int U = 8;
-    for (long long it = i0; it < i1; ++it) {
-        const int b = static_cast<int>(it / p.items_per_image);
-        const int blk = static_cast<int>(it % p.items_per_image);
-        if (b != cur_b) {                            // uniform over the CTA
-            __syncthreads();                         // everyone is done with the previous image's table
-            groupnorm_scale_shift(p, b, sc, sh, gm, gr);
-            cur_b = b;
-            if (active && !wide) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { k4[j] = sc[c + j]; s4[j] = sh[c + j]; }
-            }
-        }
-        if (!active) continue;
-        const int pix0 = blk * p.pix_per_block;
-        const int pix1 = min(pix0 + p.pix_per_block, p.HW);
+    constexpr int U = 6;
+    const int orow = p.precise ? 2 * C : C;
+    const long long lo_off = p.precise ? C : 0;
+    for (long long g = g0; g < g1;) {
+        const int b = static_cast<int>(g / p.HW);
         const long long img = static_cast<long long>(b) * p.HW;
+        const int pix0 = static_cast<int>(g - img);
+        const int pix1 = static_cast<int>((g1 - img) < p.HW ? (g1 - img) : p.HW);
+        g = img + pix1;
+        __syncthreads();                             // everyone is done with the previous image's table
+        groupnorm_scale_shift(p, b, sc, sh, gm, gr);
+        if (!active) continue;
         if (wide) {
             for (int pix = pix0; pix < pix1; ++pix) {
                 for (int v = threadIdx.x; v < vpp; v += nth) {
@@ -139,39 +138,50 @@ __device__ __forceinline__ void prep_body(const PrepParams& p, float* sm, const 
                     const float4 kk = *reinterpret_cast<const float4*>(sc + cc), ss = *reinterpret_cast<const float4*>(sh + cc);
                     float y0 = x.x * kk.x + ss.x, y1 = x.y * kk.y + ss.y, y2 = x.z * kk.z + ss.z, y3 = x.w * kk.w + ss.w;
                     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                    const long long o = (img + pix) * (p.precise ? 2 * C : C) + cc;
-                    const long long lo_off = p.precise ? C : 0;
+                    const long long o = (img + pix) * orow + cc;
                     store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);
                     if (p.out_raw) store_operand4(p.out_raw, o, lo_off, x.x, x.y, x.z, x.w);
                 }
             }
             continue;
         }
-        for (int pix = pix0 + lp; pix < pix1; pix += kpix * U) {
-            float4 x[U];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k4[j] = sc[c + j]; s4[j] = sh[c + j]; }
+        // software pipeline: the loads of batch i+1 are in flight while batch i is normalised and stored (2 x U x 16 B per thread)
+        float4 cur[U], nxt[U];
+        int pix = pix0 + lp;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int pp = pix + u * kpix;
+            if (pp < pix1) cur[u] = __ldcg(reinterpret_cast<const float4*>(src + (img + pp) * cs));
+        }
+        while (pix < pix1) {
+            const int npix = pix + kpix * U;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int pp = pix + u * kpix;
-                if (pp < pix1) x[u] = __ldcg(reinterpret_cast<const float4*>(src + (img + pp) * cs));
+                const int pp = npix + u * kpix;
+                if (pp < pix1) nxt[u] = __ldcg(reinterpret_cast<const float4*>(src + (img + pp) * cs));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int pp = pix + u * kpix;
                 if (pp < pix1) {
-                    float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
+                    float y0 = cur[u].x * k4[0] + s4[0], y1 = cur[u].y * k4[1] + s4[1], y2 = cur[u].z * k4[2] + s4[2], y3 = cur[u].w * k4[3] + s4[3];
                     if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                    const long long o = (img + pp) * (p.precise ? 2 * C : C) + c;
-                    const long long lo_off = p.precise ? C : 0;
+                    const long long o = (img + pp) * orow + c;
                     store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);
-                    if (p.out_raw) store_operand4(p.out_raw, o, lo_off, x[u].x, x[u].y, x[u].z, x[u].w);
+                    if (p.out_raw) store_operand4(p.out_raw, o, lo_off, cur[u].x, cur[u].y, cur[u].z, cur[u].w);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+            pix = npix;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------- row softmax
-__device__ __forceinline__ void softmax_body(const SoftmaxParams& p, const int cta, const int ncta) {
+__device__ __noinline__ void softmax_body(const SoftmaxParams& p, const int cta, const int ncta) {
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (long long row = static_cast<long long>(cta) * nwarp + warp; row < p.rows; row += static_cast<long long>(ncta) * nwarp) {
         const int r_in = static_cast<int>(row % p.L);
@@ -199,7 +209,7 @@ __device__ __forceinline__ void softmax_body(const SoftmaxParams& p, const int c
 // PositionalEncoding + noise_level_mlp (unet.py:18-31,177-184) and this CTA's share of the FeatureWiseAffine projections
 // (unet.py:34-50, bias-only form, block1's conv bias folded in).  Every CTA recomputes tau (32 K MACs per distinct noise level: cheaper
 // than a grid barrier); during sampling all images share the step's noise level, so tau is computed once.
-__device__ __forceinline__ void embed_film_body(const EmbedFilmParams& p, float* sm, const int t_step, const int cta, const int ncta) {
+__device__ __noinline__ void embed_film_body(const EmbedFilmParams& p, float* sm, const int t_step, const int cta, const int ncta) {
     const int inner = p.e.inner, hid = 4 * inner, B = p.B;
     const int from_table = p.e.ctl->nl_from_table;
     const int n_tau = from_table ? 1 : B;
@@ -255,11 +265,16 @@ __device__ __forceinline__ void embed_film_body(const EmbedFilmParams& p, float*
 }
 
 // ---------------------------------------------------------------------------------------------------------------- the step kernel
+// (not inlined: every tile variant / op body gets its own register allocation instead of sharing the step kernel's)
 template <int BN, int MH>
-__device__ __forceinline__ void mega_gemm(const uint8_t* hdr_params, const uint8_t* gparams, uint32_t base, uint8_t* base_ptr, uint32_t tmem_base,
+__device__ __noinline__ void mega_gemm(const uint8_t* hdr_params, const uint8_t* gparams, uint32_t base, uint8_t* base_ptr, uint32_t tmem_base,
                                           int cta, int ncta) {
     gemm_tile_body<BN, MH, true>(*reinterpret_cast<const GemmParams*>(hdr_params), reinterpret_cast<const GemmParams*>(gparams), base, base_ptr,
                                  tmem_base, cta, ncta);
+}
+
+__device__ __noinline__ void mega_attn(const AttnParams& ap, const AttnParams* gp, uint32_t base, uint8_t* base_ptr, uint32_t tmem_base, int qt, int dc, int z) {
+    attn_unit<true>(ap, gp, base, base_ptr, tmem_base, qt, dc, z);
 }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_constant__ MegaParams mp) {
@@ -294,6 +309,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_cons
     for (int i = 0; i < mp.n_ops; ++i) {
         const MegaOp op = mp.ops[i];
         const uint8_t* gparams = mp.blob + op.param_off;
+        const bool stamp = mp.prof && cta == 0 && threadIdx.x == 0;
+        if (stamp) mp.prof[4 * i] = globaltimer_ns();
         if (op.sync_before) gb.arrive();         // (starts with a __syncthreads: the previous op is finished in this CTA)
         // CTA-local set-up, overlapped with the other CTAs still arriving: parameter block -> shared-memory header, and for a tile op its
         // stage table / descriptor prefetch / mbarrier recycling
@@ -305,8 +322,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_cons
             gemm_stage_setup(*reinterpret_cast<const GemmParams*>(hdr_params), reinterpret_cast<const GemmParams*>(gparams), base, base_ptr,
                              op.variant & 0xffff, true);
         }
+        if (stamp) mp.prof[4 * i + 1] = globaltimer_ns();
         if (op.sync_before) gb.wait(i); else __syncthreads();
-        if (mp.prof && cta == 0 && threadIdx.x == 0) mp.prof[i] = globaltimer_ns();
+        if (stamp) mp.prof[4 * i + 2] = globaltimer_ns();
         switch (op.type) {
             case MOP_GEMM: {
                 switch (op.variant) {
@@ -329,7 +347,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_cons
                 const int n_dc = ap.C / ap.dn, per_z = (ap.Lt / 128) * n_dc, units = per_z * ap.nz;
                 for (int u = cta; u < units; u += ncta) {
                     const int z = u / per_z, r = u % per_z;
-                    attn_unit<true>(ap, reinterpret_cast<const AttnParams*>(gparams), base, base_ptr, tmem_base, r / n_dc, r % n_dc, z);
+                    mega_attn(ap, reinterpret_cast<const AttnParams*>(gparams), base, base_ptr, tmem_base, r / n_dc, r % n_dc, z);
                 }
                 break;
             }
@@ -347,12 +365,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) step_kernel(const __grid_cons
             }
             default: break;
         }
-        __threadfence();
+        if (stamp) mp.prof[4 * i + 3] = globaltimer_ns();
+        // Publication of this op's global writes: the next arrive() is __syncthreads + (thread 0) __threadfence + release -- cumulative over
+        // the writes of the whole CTA, as in cooperative-groups grid.sync; each thread orders its own generic writes against later
+        // async-proxy (TMA) accesses itself.
         fence_proxy_async_all();
         __syncthreads();
     }
     if (cta == 0 && threadIdx.x == 0) {
-        if (mp.prof) mp.prof[mp.n_ops] = globaltimer_ns();
+        if (mp.prof) mp.prof[4 * mp.n_ops] = globaltimer_ns();
         mp.ctl->t_cur = t_step;               // what the per-layer path's step_begin_kernel does at the start of a step
         mp.ctl->t_next = t_step - 1;
     }

@@ -127,7 +127,9 @@ int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the 
 int sr3_engine_uses_step_kernel(const sr3_engine* e);
 /* Per-op device time (us) of the most recent step-kernel launch: globaltimer stamps taken by CTA 0 after each grid barrier.
  * types: 0 tensor-core tile loop, 1 GroupNorm apply, 2 fused attention, 3 row softmax, 4 embedding + FiLM, 5 statistics clear. */
-int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, int* n_ops, void* stream);
+int sr3_engine_step_kernel_profile(sr3_engine* e, int cap, int* types, double* us, double* phases_or_null, int* n_ops, void* stream);
+/* phases (optional, [cap][4] us): per op, time CTA 0 spent in set-up (barrier arrive + parameter / stage-table copy), waiting at the grid
+ * barrier, in the op body, and in the end-of-op fence. */
 int64_t sr3_engine_workspace_bytes(const sr3_engine* e);
 /* Per-kernel timing of one eager (non-graph) reverse step at timestep t, averaged over `reps` repetitions after one warm-up,
  * CUDA events on `stream` around every launch.  kinds: 0 tensor-core tile kernel, 1 GroupNorm apply, 2 cast/upsample,

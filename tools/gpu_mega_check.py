@@ -63,6 +63,13 @@ def run(name, unet, size, B, K=20):
             res["mega"]["ops"] = {k: [v[0], round(v[1], 1)] for k, v in by.items()}
             res["mega"]["ops_total_us"] = round(sum(us for _, us in prof), 1)
             res["mega"]["per_op_us"] = [[t, round(us, 1)] for t, us in prof]
+            ph = eng.step_kernel_profile(phases=True)
+            agg = {}
+            for t, us, p4 in ph:
+                d = agg.setdefault(eng.STEP_OP_NAMES[t], [0.0, 0.0, 0.0, 0.0])
+                for k in range(4):
+                    d[k] += p4[k]
+            res["mega"]["phase_us(setup,wait,body,fence)"] = {k: [round(x, 1) for x in v] for k, v in agg.items()}
         del eng, net
         torch.cuda.empty_cache()
     res["eps_bit_equal"] = bool(torch.equal(outs[True][0], outs[False][0]))
