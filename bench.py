@@ -424,9 +424,19 @@ def main():
             d["ops"] += 1
             d["us"] = round(d["us"] + us, 2)
     else:
-        prof = eng.profile_step(1000, reps=3)
-        kernel_name = "gemm_tile_kernel + attn_kernel (per-layer path)"
+        prof = eng.profile_step(1000, reps=3)          # eager step, CUDA events around every launch on the launching stream
+        kinds = {0: "gemm_tile_kernel", 1: "prep_kernel(groupnorm+silu)", 2: "cast_kernel", 3: "softmax_kernel", 4: "other", 5: "attn_kernel"}
+        n_tc = sum(1 for k, _, _, _ in prof if k in (0, 5))
+        kernel_name = "gemm_tile_kernel + attn_kernel: the %d tensor-core launches of one step (per-layer path, summed per-launch event times)" % n_tc
         kernel_ms = sum(m for k, m, _, _ in prof if k in (0, 5))
+        by_op = {}
+        for k, m, fl, by in prof:
+            d = by_op.setdefault(kinds[k], {"launches": 0, "us": 0.0, "bytes": 0.0})
+            d["launches"] += 1
+            d["us"] = round(d["us"] + m * 1e3, 2)
+            d["bytes"] += by
+        for d in by_op.values():
+            d["GB_per_s"] = round(d.pop("bytes") / (d["us"] * 1e-6) / 1e9, 1) if d["us"] > 0 else None
     achieved = alg_flops_step / (kernel_ms * 1e-3) / 1e12
     traffic, traffic_src = None, None
     for cand in ("r02_traffic.json", "r01_traffic.json"):
@@ -442,7 +452,8 @@ def main():
             "peak_source": peaks["src"] + ": frac is against the BURST bf16 figure", "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_flops_per_launch": alg_flops_step, "algorithmic_bytes_per_launch": 2.98e9 * per / 16.0,
             "kernel_ms_per_launch": kernel_ms, "launches_per_step": eng.launches_per_step(), "ops_per_step": eng.ops_per_step(),
-            "frac_of_nominal_bound": (0.732 * per / 16.0) / (ms / K) if per == 16 else None, "by_op": by_op}
+            "frac_of_nominal_bound": (0.732 * per / 16.0) / (ms / K) if per == 16 else None,
+            "step_frac_of_burst_peak": (alg_flops_step / (ms / K * 1e-3) / 1e12) / peaks["burst"], "by_op": by_op}
     if args.profile_out:
         os.makedirs(os.path.dirname(os.path.abspath(args.profile_out)), exist_ok=True)
         json.dump({"per_op": [{"op": eng.STEP_OP_NAMES[t], "us": us} for t, us in (step_prof or [])], "summary": roof}, open(args.profile_out, "w"), indent=1)
