@@ -47,6 +47,8 @@ _SIGS = {
     "sr3_read_state": (c_int, [c_void_p, c_void_p, c_void_p]),
     "sr3_engine_profile_step": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_int), POINTER(c_float), POINTER(c_double), POINTER(c_double),
                                         POINTER(c_int), c_void_p]),
+    "sr3_pil_bicubic_tables": (c_int, [c_int, c_int, POINTER(c_int), POINTER(c_int), c_int, POINTER(c_int)]),
+    "sr3_resize_bicubic_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "sr3_tensor2img": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p]),
     "sr3_ssd_u8": (c_int, [c_void_p, c_void_p, c_int64, POINTER(c_uint64), c_void_p]),
     "sr3_engine_num_launches_per_step": (c_int, [c_void_p]),

@@ -455,4 +455,34 @@ __global__ void __launch_bounds__(256) ssd_u8_kernel(const unsigned char* __rest
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+// One pass of Pillow's 8-bit resampler (src/libImaging/Resample.c, ImagingResampleHorizontal_8bpc / Vertical_8bpc) with host-built
+// integer coefficient tables: out = clip8((2^21 + sum_k in[first + k] * coef[k]) >> 22).  `axis_stride` / `line_stride` / `img_stride` are in
+// elements of the uint8 input [img][line][axis][C]; one thread per output element (img, line, o, c).
+// Output: uint8 [img][..][C] with the same structure (dst_u8) and / or float CHW planes (dst_f32: ToTensor /255, optional flip along W,
+// * (max - min) + min -- data/util.py:74-83) -- only meaningful for the LAST pass (vertical), where line = x and o = y.
+__global__ void __launch_bounds__(256) resample_u8_kernel(const unsigned char* __restrict__ src, unsigned char* __restrict__ dst_u8, float* __restrict__ dst_f32,
+                                                          int n_img, int n_line, int n_out, int C, long long in_axis_stride, long long in_line_stride,
+                                                          long long in_img_stride, long long out_axis_stride, long long out_line_stride, long long out_img_stride,
+                                                          const int* __restrict__ bounds, const int* __restrict__ coef, int ksize, int flip, float vmin, float vmax) {
+    const long long total = static_cast<long long>(n_img) * n_line * n_out * C;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int c = static_cast<int>(i % C);
+        const int line = static_cast<int>((i / C) % n_line);
+        const int o = static_cast<int>((i / (static_cast<long long>(C) * n_line)) % n_out);
+        const int img = static_cast<int>(i / (static_cast<long long>(C) * n_line * n_out));
+        const int first = bounds[2 * o], n = bounds[2 * o + 1];
+        const unsigned char* sp = src + img * in_img_stride + line * in_line_stride + first * in_axis_stride + c;
+        int acc = 1 << 21;
+        for (int k = 0; k < n; ++k) acc += static_cast<int>(sp[k * in_axis_stride]) * coef[o * ksize + k];
+        int v = acc >> 22;
+        v = v < 0 ? 0 : (v > 255 ? 255 : v);
+        if (dst_u8) dst_u8[img * out_img_stride + line * out_line_stride + o * out_axis_stride + c] = static_cast<unsigned char>(v);
+        if (dst_f32) {                                 // last (vertical) pass: o = y, line = x; CHW planes of n_out x n_line
+            const int x = flip ? (n_line - 1 - line) : line;
+            const float t = __fdiv_rn(static_cast<float>(v), 255.0f);
+            dst_f32[((static_cast<long long>(img) * C + c) * n_out + o) * n_line + x] = __fadd_rn(__fmul_rn(t, __fsub_rn(vmax, vmin)), vmin);
+        }
+    }
+}
+
 }  // namespace sr3

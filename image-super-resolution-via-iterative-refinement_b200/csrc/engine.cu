@@ -1768,6 +1768,101 @@ int sr3_tensor2img(const float* src, unsigned char* dst, int n, int C, int H, in
     API_END
 }
 
+}  // extern "C"
+
+namespace {
+// Pillow's Resample.c: precompute_coeffs (bicubic filter, a = -0.5, support 2) + normalize_coeffs_8bpc (PRECISION_BITS = 22), whole input range
+double pil_bicubic_filter(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+    if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+    return 0.0;
+}
+void pil_bicubic_tables(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& coef, int& ksize) {
+    const double scale = (double)in_size / out_size;
+    double filterscale = scale;
+    if (filterscale < 1.0) filterscale = 1.0;
+    const double support = 2.0 * filterscale;
+    ksize = (int)ceil(support) * 2 + 1;
+    bounds.assign((size_t)out_size * 2, 0);
+    coef.assign((size_t)out_size * ksize, 0);
+    const double ss = 1.0 / filterscale;
+    std::vector<double> w((size_t)ksize);
+    for (int xx = 0; xx < out_size; ++xx) {
+        const double center = 0.0 + (xx + 0.5) * scale;
+        int xmin = (int)(center - support + 0.5);
+        if (xmin < 0) xmin = 0;
+        int xmax = (int)(center + support + 0.5);
+        if (xmax > in_size) xmax = in_size;
+        xmax -= xmin;
+        double ww = 0.0;
+        for (int x = 0; x < xmax; ++x) { w[x] = pil_bicubic_filter((x + xmin - center + 0.5) * ss); ww += w[x]; }
+        for (int x = 0; x < xmax; ++x) {
+            const double v = (ww != 0.0) ? w[x] / ww : w[x];
+            coef[(size_t)xx * ksize + x] = v < 0 ? (int)(-0.5 + v * (1 << 22)) : (int)(0.5 + v * (1 << 22));
+        }
+        bounds[2 * xx] = xmin; bounds[2 * xx + 1] = xmax;
+    }
+}
+}  // namespace
+
+extern "C" {
+
+// Host-only: the integer coefficient tables of one resampling pass (needs no GPU; checked against Pillow's by the CPU test-suite).
+int sr3_pil_bicubic_tables(int in_size, int out_size, int* bounds, int* coef, int coef_cap, int* ksize) {
+    API_BEGIN
+    REQUIRE(in_size >= 1 && out_size >= 1 && bounds && coef && ksize, "bad arguments");
+    std::vector<int> b, c;
+    int ks = 0;
+    pil_bicubic_tables(in_size, out_size, b, c, ks);
+    REQUIRE((int)c.size() <= coef_cap, "coefficient buffer too small (%d needed)", (int)c.size());
+    memcpy(bounds, b.data(), b.size() * sizeof(int));
+    memcpy(coef, c.data(), c.size() * sizeof(int));
+    *ksize = ks;
+    API_END
+}
+
+// data/prepare_data.py:17-40 (`trans_fn.resize(img, size, Image.BICUBIC)`: Pillow's two-pass fixed-point bicubic resampler) and
+// data/util.py:74-83 (ToTensor, optional horizontal flip, range mapping) on the device.  src uint8 DEVICE [B][h][w][C] (HWC, as PIL hands
+// it over); dst_u8 (optional) uint8 DEVICE [B][H][W][C]; dst_f32 (optional) fp32 DEVICE [B][C][H][W] = (resized / 255) * (max - min) + min,
+// mirrored along W when flip != 0.  Integer-exact against Pillow.
+int sr3_resize_bicubic_u8(const unsigned char* src, unsigned char* dst_u8, float* dst_f32, int B, int h, int w, int C, int H, int W, int flip,
+                          float min_v, float max_v, void* stream) {
+    API_BEGIN
+    REQUIRE(src && (dst_u8 || dst_f32) && B >= 1 && h >= 1 && w >= 1 && C >= 1 && C <= 4 && H >= 1 && W >= 1, "bad resize arguments");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    DevAllocs mem;
+    std::vector<int> bh, ch, bv, cv;
+    int ksh = 0, ksv = 0;
+    pil_bicubic_tables(w, W, bh, ch, ksh);
+    pil_bicubic_tables(h, H, bv, cv, ksv);
+    auto up = [&](const std::vector<int>& v) {
+        int* d = static_cast<int*>(mem.alloc(v.size() * sizeof(int), false));
+        CK(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        return d;
+    };
+    int *dbh = up(bh), *dch = up(ch), *dbv = up(bv), *dcv = up(cv);
+    // horizontal pass first (Pillow's order): [B][h][w][C] -> tmp [B][h][W][C]; then vertical: -> [B][H][W][C] (+ float planes)
+    unsigned char* tmp = static_cast<unsigned char*>(mem.alloc((size_t)B * h * W * C, false));
+    {
+        const long long total = 1LL * B * h * W * C;
+        resample_u8_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+            src, tmp, nullptr, B, /*lines*/ h, /*out*/ W, C, /*in axis*/ C, /*in line*/ 1LL * w * C, /*in img*/ 1LL * h * w * C,
+            /*out axis*/ C, /*out line*/ 1LL * W * C, /*out img*/ 1LL * h * W * C, dbh, dch, ksh, 0, 0.f, 1.f);
+        CK(cudaGetLastError());
+    }
+    {
+        const long long total = 1LL * B * W * H * C;
+        resample_u8_kernel<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+            tmp, dst_u8, dst_f32, B, /*lines = x*/ W, /*out = y*/ H, C, /*in axis (y)*/ 1LL * W * C, /*in line (x)*/ C, /*in img*/ 1LL * h * W * C,
+            /*out axis*/ 1LL * W * C, /*out line*/ C, /*out img*/ 1LL * H * W * C, dbv, dcv, ksv, flip, min_v, max_v);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(st));             // the tables / intermediate die with this call
+    API_END
+}
+
 // calculate_psnr (core/metrics.py:42-50): returns the exact integer sum of squared differences of two uint8 DEVICE images through *ssd_host.
 int sr3_ssd_u8(const unsigned char* a, const unsigned char* b, int64_t n, unsigned long long* ssd_host, void* stream) {
     API_BEGIN

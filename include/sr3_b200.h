@@ -119,6 +119,16 @@ int sr3_tensor2img(const float* src, unsigned char* dst_u8, int n, int C, int H,
  * PSNR = 20 log10(255 / sqrt(ssd / n)) is formed by the caller in float64 as the reference does. */
 int sr3_ssd_u8(const unsigned char* a_u8, const unsigned char* b_u8, int64_t n, unsigned long long* ssd_host, void* stream);
 
+/* Entrance of the path: the conditioning image.  data/prepare_data.py:17-40 `trans_fn.resize(img, size, Image.BICUBIC)` (Pillow's two-pass
+ * fixed-point bicubic resampler on uint8) + data/util.py:74-83 `transform_augment` (ToTensor, optional horizontal flip, range mapping).
+ * src uint8 DEVICE [B][h][w][C] (HWC); dst_u8 (optional) uint8 DEVICE [B][H][W][C]; dst_f32 (optional) fp32 DEVICE [B][C][H][W] =
+ * (resized / 255) * (max_v - min_v) + min_v, mirrored along W when flip != 0.  Integer-exact against Pillow 12. */
+/* Host-only helper: Pillow's integer coefficient tables of one bicubic pass in_size -> out_size (bounds [out][2] = first tap, tap count;
+ * coef [out][ksize], 22 fractional bits). */
+int sr3_pil_bicubic_tables(int in_size, int out_size, int* bounds, int* coef, int coef_cap, int* ksize);
+int sr3_resize_bicubic_u8(const unsigned char* src_u8, unsigned char* dst_u8, float* dst_f32, int B, int h, int w, int C, int H, int W, int flip,
+                          float min_v, float max_v, void* stream);
+
 /* Introspection for tests / bench. */
 int sr3_engine_num_launches_per_step(const sr3_engine* e);   /* kernel launches per reverse step: 1 with the persistent step kernel */
 int sr3_engine_num_ops_per_step(const sr3_engine* e);        /* launches of the per-layer path (the default; also what sr3_engine_profile_step times) */

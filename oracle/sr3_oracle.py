@@ -499,3 +499,101 @@ def calculate_psnr(img1: np.ndarray, img2: np.ndarray) -> float:
     if mse == 0:
         return float("inf")
     return 20 * math.log10(255.0 / math.sqrt(mse))
+
+
+# --------------------------------------------------------------------------------------
+# entrance of the sampling path: the conditioning image.  data/prepare_data.py:17-40 builds it as
+#   sr_img = trans_fn.resize(lr_img, 128, Image.BICUBIC)      (PIL: Pillow's two-pass fixed-point resampler on uint8 RGB)
+# and data/util.py:74-83 turns it into the network input: ToTensor (uint8 / 255) -> optional horizontal flip -> * (max - min) + min.
+# Pillow is a third-party dependency of the reference (requirement.txt: "pillow"; the build container has 12.2.0); the algorithm below
+# restates its src/libImaging/Resample.c (precompute_coeffs, normalize_coeffs_8bpc, ImagingResampleHorizontal_8bpc / Vertical_8bpc)
+# and is pinned against PIL itself in tests/test_data_pipeline.py.
+# --------------------------------------------------------------------------------------
+PIL_PRECISION_BITS = 32 - 8 - 2
+
+
+def _pil_bicubic(x: float) -> float:
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_tables(in_size: int, out_size: int):
+    """Resample.c precompute_coeffs + normalize_coeffs_8bpc for the bicubic filter (support 2) over the whole input range:
+    -> (bounds int32 [out][2] = (first input pixel, tap count), coefficients int32 [out][ksize], ksize)."""
+    scale = filterscale = float(in_size) / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((out_size, 2), dtype=np.int32)
+    kk = np.zeros((out_size, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = 0.0 + (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        w = [_pil_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for v in w:
+            ww += v
+        if ww != 0.0:
+            w = [v / ww for v in w]
+        for x, v in enumerate(w):
+            kk[xx, x] = int(-0.5 + v * (1 << PIL_PRECISION_BITS)) if v < 0 else int(0.5 + v * (1 << PIL_PRECISION_BITS))
+        bounds[xx] = (xmin, xmax)
+    return bounds, kk, ksize
+
+
+def pil_resize_bicubic(img: np.ndarray, out_h: int, out_w: int) -> np.ndarray:
+    """Image.resize((out_w, out_h), Image.BICUBIC) of a uint8 HWC image: horizontal pass, then vertical pass, each rounding to uint8
+    (ImagingResample: both passes are needed whenever the size changes in that direction)."""
+    h, w, c = img.shape
+    cur = img.astype(np.int64)
+    if out_w != w:
+        b, kk, _ = pil_bicubic_tables(w, out_w)
+        nxt = np.empty((h, out_w, c), dtype=np.int64)
+        for xx in range(out_w):
+            x0, n = int(b[xx, 0]), int(b[xx, 1])
+            acc = np.full((h, c), 1 << (PIL_PRECISION_BITS - 1), dtype=np.int64)
+            for x in range(n):
+                acc += cur[:, x0 + x, :] * int(kk[xx, x])
+            nxt[:, xx, :] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+        cur = nxt
+    if out_h != h:
+        b, kk, _ = pil_bicubic_tables(h, out_h)
+        nxt = np.empty((out_h, cur.shape[1], c), dtype=np.int64)
+        for yy in range(out_h):
+            y0, n = int(b[yy, 0]), int(b[yy, 1])
+            acc = np.full((cur.shape[1], c), 1 << (PIL_PRECISION_BITS - 1), dtype=np.int64)
+            for y in range(n):
+                acc += cur[y0 + y, :, :] * int(kk[yy, y])
+            nxt[yy, :, :] = np.clip(acc >> PIL_PRECISION_BITS, 0, 255)
+        cur = nxt
+    return cur.astype(np.uint8)
+
+
+def transform_augment(imgs_u8: Sequence[np.ndarray], split: str = "val", min_max=(0, 1), flip: bool = False) -> List[Tensor]:
+    """data/util.py:74-83 with the random draw of RandomHorizontalFlip injected (`flip`): uint8 HWC -> float CHW in [min, max]."""
+    out = []
+    for im in imgs_u8:
+        t = torch.from_numpy(np.ascontiguousarray(im)).permute(2, 0, 1).float().div(255)       # torchvision ToTensor
+        if split == "train" and flip:
+            t = t.flip(-1)
+        out.append(t * (min_max[1] - min_max[0]) + min_max[0])
+    return out
+
+
+def lr_to_sr_input(lr_u8: np.ndarray, size: int, min_max=(-1, 1), flip: bool = False) -> Tensor:
+    """prepare_data.py:32-34 (sr = bicubic resize of lr to `size`) + util.py:74-83 with split/flip as above: uint8 [h,w,3] -> float [3,size,size]."""
+    return transform_augment([pil_resize_bicubic(lr_u8, size, size)], "train" if flip else "val", min_max, flip)[0]
