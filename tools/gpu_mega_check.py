@@ -79,6 +79,7 @@ def run(name, unet, size, B, K=20):
     po = res["mega"].pop("per_op_us")
     print(name, "B=%d" % B, json.dumps(res), flush=True)
     print("   per-op us:", po, flush=True)
+    res["mega"]["per_op_us"] = po
     return res
 
 
