@@ -185,14 +185,33 @@ void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cuda
     cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 1 : 0;
     CK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
+// Split-K layers: the `ksplit` CTAs that share an output tile are consecutive blocks and wait for each other inside the kernel.  They are
+// launched as ONE THREAD-BLOCK CLUSTER (cluster dimension = ksplit): the hardware gang-schedules a cluster, so the partners are co-resident
+// by construction -- no assumption about what else occupies the device (other engines / streams, NCCL, library kernels), inside or outside
+// graph capture, and the launch keeps its programmatic-dependent-launch edge.  SR3_NO_CLUSTER=1: the round-1 form (plain launch inside
+// graphs, cooperative launch outside).
+bool use_cluster_split() { static int v = -1; if (v < 0) v = getenv("SR3_NO_CLUSTER") ? 0 : 1; return v == 1; }
+constexpr int MAX_CLUSTER_SPLIT = 8;               // portable cluster size limit
 template <int BN, int MH>
 void launch_gemm_bn(const GemmParams& p, dim3 grid, int smem, cudaStream_t st) {
+    if (p.ksplit > 1 && use_cluster_split()) {
+        REQUIRE(p.ksplit <= MAX_CLUSTER_SPLIT && grid.x % p.ksplit == 0, "split-K factor %d does not form clusters of grid %u", p.ksplit, grid.x);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)p.ksplit; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = use_pdl() ? 2 : 1;
+        CK(cudaLaunchKernelEx(&cfg, gemm_tile_kernel<BN, MH>, p));
+        return;
+    }
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (p.ksplit > 1) CK(cudaStreamIsCapturing(st, &cap));
     if (p.ksplit > 1 && cap == cudaStreamCaptureStatusNone && getenv("SR3_NO_COOP") == nullptr) {
-        // split-K CTAs wait for their partners inside the kernel: launch cooperatively so that the runtime guarantees co-residency
-        // (or fails the launch) even when another stream / engine / library kernel holds SMs.  No PDL overlap for these launches.
-        // (Launches being captured into the per-layer step graph keep the plain form: that graph runs alone on its stream.)
+        // (SR3_NO_CLUSTER) split-K CTAs wait for their partners inside the kernel: launch cooperatively so that the runtime guarantees
+        // co-residency (or fails the launch) even when another stream / engine / library kernel holds SMs.  No PDL overlap for these launches.
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid; cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = (size_t)smem; cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -215,6 +234,40 @@ void init_gemm_attrs() {
     CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     CK(cudaFuncSetAttribute(gemm_tile_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+}
+
+// How many clusters of `c` tile-kernel CTAs (one CTA per SM: they use the whole shared memory) the device holds at once; a cluster lives
+// inside one GPC, so this is less than SMs / c.  Split-K factors are chosen so that all clusters of a layer run in one wave.
+int cluster_capacity(int c) {
+    static std::map<std::pair<int, int>, int> cache;
+    static std::mutex mu;
+    if (c <= 1) return num_sms();
+    init_gemm_attrs();
+    std::lock_guard<std::mutex> lock(mu);
+    const std::pair<int, int> key(current_device(), c);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(c * 32); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = SMEM_LIMIT;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tile_kernel<64, 1>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = 8 * ((num_sms() / 8) / c);               // eight GPCs of equal size, conservatively
+    }
+    if (const char* e = getenv("SR3_CLUSTER_DEBUG")) { if (atoi(e)) fprintf(stderr, "sr3: cluster_capacity(%d) = %d\n", c, n); }
+    cache[key] = n;
+    return n;
+}
+// largest split-K factor <= want whose clusters all fit the device together with `tiles` output tiles
+int fit_split(int want, long long tiles) {
+    if (!use_cluster_split()) return want;
+    if (want > MAX_CLUSTER_SPLIT) want = MAX_CLUSTER_SPLIT;
+    while (want > 1 && cluster_capacity(want) < tiles) --want;
+    return want;
 }
 
 struct DevAllocs {
@@ -390,6 +443,7 @@ Op make_gemm_op(const GemmDesc& d, DevAllocs& mem) {
             if (want > p.num_k * d.passes / 2) want = p.num_k * d.passes / 2;    // at least two stages per slice
             const int units = d.mh * (d.block_n / 32) * 4; // 32x32 units of a tile: every split finalises at least one
             if (want > units) want = units;
+            want = fit_split(want, tiles);
             if (want > 1) {
                 p.ksplit = want;
                 p.ws = static_cast<float*>(mem.alloc((size_t)tiles * want * d.mh * 128 * d.block_n * sizeof(float), false));
@@ -483,6 +537,7 @@ void conv_geometry(GemmDesc& d, int OW, int OH, int Bp, int cout, bool has_resid
             if (smax > nstage / 2) smax = nstage / 2;
             if (smax > 16) smax = 16;
             if (smax < 1) smax = 1;
+            smax = fit_split(smax, tiles);
         }
         split = smax;
         const long long waves = (tiles * smax + sms - 1) / sms;

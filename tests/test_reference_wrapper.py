@@ -100,7 +100,8 @@ def test_reference_ddpm_wrapper_samples_on_the_gpu(ref_model_pkg, tmp_path):
     vis = m.get_current_visuals()
     n_snap = len([i for i in range(SCHED["n_timestep"]) if i % (1 | (SCHED["n_timestep"] // 10)) == 0])
     assert vis["SR"].shape == (2 * (1 + n_snap), 3, 32, 32) and vis["SR"].device.type == "cpu" and torch.isfinite(vis["SR"]).all()
-    assert torch.equal(vis["SR"][:2], data["SR"]) and torch.equal(vis["INF"], data["SR"]) and torch.equal(vis["HR"], data["HR"])
+    # (feed_data moved the entries of `data` to the GPU in place: base_model.py:29-40)
+    assert torch.equal(vis["SR"][:2], data["SR"].cpu()) and torch.equal(vis["INF"], data["SR"].cpu()) and torch.equal(vis["HR"], data["HR"].cpu())
     m.test(continous=False)
     last = m.get_current_visuals()["SR"]
     assert last.shape == (3, 32, 32) and torch.isfinite(last).all()       # the reference returns ret_img[-1]: the last image only (diffusion.py:198-200)
