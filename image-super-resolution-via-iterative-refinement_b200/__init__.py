@@ -7,6 +7,7 @@ from .model import networks  # noqa: F401
 from .model.networks import define_G  # noqa: F401
 from .model.sr3_modules.diffusion import GaussianDiffusion  # noqa: F401
 from .model.sr3_modules.unet import UNet  # noqa: F401
+from .optim import FusedAdam  # noqa: F401
 
-__all__ = ["define_G", "networks", "GaussianDiffusion", "UNet"]
+__all__ = ["define_G", "networks", "GaussianDiffusion", "UNet", "FusedAdam"]
 __version__ = "0.1.0"

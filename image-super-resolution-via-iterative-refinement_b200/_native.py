@@ -29,6 +29,18 @@ _SIGS = {
     "sr3_last_error": (c_char_p, []),
     "sr3_abi_version": (c_int, []),
     "sr3_engine_create": (c_int, [POINTER(UNetConfigC), c_int, c_int, POINTER(c_void_p)]),
+    "sr3_engine_create_train": (c_int, [POINTER(UNetConfigC), c_int, c_int, c_float, POINTER(c_void_p)]),
+    "sr3_train_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_uint64, POINTER(c_double), c_void_p]),
+    "sr3_train_backward": (c_int, [c_void_p, c_float, POINTER(c_void_p), c_int, c_void_p]),
+    "sr3_train_num_backward_blocks": (c_int, [c_void_p]),
+    "sr3_train_backward_begin": (c_int, [c_void_p, c_float, POINTER(c_void_p), c_int]),
+    "sr3_train_backward_block": (c_int, [c_void_p, c_int, c_void_p]),
+    "sr3_train_backward_finish": (c_int, [c_void_p, c_void_p]),
+    "sr3_train_block_params": (c_int, [c_void_p, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
+    "sr3_train_set_dropout_mask": (c_int, [c_void_p, c_char_p, c_void_p]),
+    "sr3_train_num_dropout_layers": (c_int, [c_void_p]),
+    "sr3_train_dropout_layer_name": (c_int, [c_void_p, c_int, c_char_p, c_int]),
+    "sr3_adam_step": (c_int, [c_void_p, c_int, c_float, c_float, c_float, c_float, c_int, c_float, c_void_p]),
     "sr3_engine_destroy": (None, [c_void_p]),
     "sr3_engine_num_params": (c_int, [c_void_p]),
     "sr3_engine_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
@@ -112,7 +124,9 @@ def _f32c(t, device):
 class Engine:
     """One (config, batch, device) instance of the native plan: packed weights + activations + captured step graph."""
 
-    def __init__(self, cfg: dict, batch: int, device: torch.device):
+    def __init__(self, cfg: dict, batch: int, device: torch.device, train_dropout=None):
+        """train_dropout: None = inference plan; a float = TRAINING plan (forward keeps every intermediate, backward recorded) with that
+        Dropout probability (sr3_engine_create_train)."""
         if device.type != "cuda":
             raise NativeLibraryError("sr3_b200 runs on a CUDA (sm_100a) device only; got device=%s" % device)
         self.device = device
@@ -138,8 +152,13 @@ class Engine:
         c.precision = PRECISIONS[self.precision]
         self._h = c_void_p()
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        _check(lib().sr3_engine_create(ctypes.byref(c), batch, idx, ctypes.byref(self._h)))
+        self.train_dropout = train_dropout
+        if train_dropout is None:
+            _check(lib().sr3_engine_create(ctypes.byref(c), batch, idx, ctypes.byref(self._h)))
+        else:
+            _check(lib().sr3_engine_create_train(ctypes.byref(c), batch, idx, float(train_dropout), ctypes.byref(self._h)))
         self.T = 0
+        self._keep = []
 
     def __del__(self):
         try:
@@ -225,6 +244,69 @@ class Engine:
         with torch.cuda.device(self.device):
             _check(lib().sr3_p_losses(self._h, _ptr(hr), _ptr(s), _ptr(g), _ptr(noise), 1 if loss_type == "l1" else 2, ctypes.byref(out), _stream()))
         return out.value
+
+    # ---- training step (model/model.py:48-58): forward with the draws injected, backward into caller-owned gradient tensors
+    def train_forward(self, hr, sr, gamma, noise, loss_type="l1", dropout_seed=0, want_loss=True):
+        hr, noise = _f32c(hr, self.device), _f32c(noise, self.device)
+        s = None if sr is None else _f32c(sr, self.device)
+        g = _f32c(gamma, self.device).reshape(-1)
+        self._keep = [hr, noise, s, g]
+        out = c_double()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_forward(self._h, _ptr(hr), _ptr(s), _ptr(g), _ptr(noise), 1 if loss_type == "l1" else 2, int(dropout_seed),
+                                           ctypes.byref(out) if want_loss else None, _stream()))
+        return out.value if want_loss else None
+
+    def _grad_ptrs(self, grads):
+        arr = (c_void_p * len(grads))()
+        for i, gten in enumerate(grads):
+            assert gten.is_cuda and gten.dtype == torch.float32 and gten.is_contiguous()
+            arr[i] = gten.data_ptr()
+        return arr
+
+    def train_backward(self, grad_scale, grads):
+        """grads: one contiguous fp32 CUDA tensor per parameter, in param_table() order; overwritten."""
+        arr = self._grad_ptrs(grads)
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_backward(self._h, float(grad_scale), arr, len(grads), _stream()))
+
+    def num_backward_blocks(self):
+        return lib().sr3_train_num_backward_blocks(self._h)
+
+    def backward_begin(self, grad_scale, grads):
+        self._grad_arr = self._grad_ptrs(grads)
+        _check(lib().sr3_train_backward_begin(self._h, float(grad_scale), self._grad_arr, len(grads)))
+
+    def backward_block(self, i):
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_backward_block(self._h, int(i), _stream()))
+
+    def backward_finish(self):
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_backward_finish(self._h, _stream()))
+
+    def block_params(self, i):
+        cap = 64
+        idx = (c_int * cap)()
+        n = c_int()
+        _check(lib().sr3_train_block_params(self._h, int(i), idx, cap, ctypes.byref(n)))
+        return [idx[k] for k in range(min(n.value, cap))]
+
+    def dropout_layers(self):
+        out = []
+        buf = ctypes.create_string_buffer(256)
+        for i in range(lib().sr3_train_num_dropout_layers(self._h)):
+            _check(lib().sr3_train_dropout_layer_name(self._h, i, buf, 256))
+            out.append(buf.value.decode())
+        return out
+
+    def set_dropout_mask(self, block_name, mask_nchw_u8):
+        """Tests: inject the keep-mask (uint8 CUDA [B,C,H,W], 1 = keep) of the nn.Dropout of `block_name` ("downs.1.res_block.block2")."""
+        if mask_nchw_u8 is not None:
+            assert mask_nchw_u8.is_cuda and mask_nchw_u8.dtype == torch.uint8 and mask_nchw_u8.is_contiguous()
+            self._keep_masks = getattr(self, "_keep_masks", {})
+            self._keep_masks[block_name] = mask_nchw_u8
+        _check(lib().sr3_train_set_dropout_mask(self._h, block_name.encode(), _ptr(mask_nchw_u8)))
 
     def p_sample_loop(self, condition_x, x_T, noises=None, seed=0, first_index=0, want_snapshots=True):
         c = None if condition_x is None else _f32c(condition_x, self.device)
@@ -349,3 +431,8 @@ def test_conv_groupnorm(x_nhwc_bf16, w_oihw, bias, gamma, beta, groups, silu, ks
     _check(lib().sr3_test_conv_groupnorm(_ptr(x_nhwc_bf16), _ptr(w_oihw), _ptr(bias), _ptr(gamma), _ptr(beta), groups, int(silu), _ptr(y), _ptr(a),
                                          B, H, W, Cin, Cout, ksize, _stream()))
     return y, a
+
+
+def adam_step(table_dev, n_tensors, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """torch.optim.Adam step over a device table of {param, grad, exp_avg, exp_avg_sq, numel} records (int64 [n, 5]) in one launch."""
+    _check(lib().sr3_adam_step(_ptr(table_dev), int(n_tensors), float(lr), float(beta1), float(beta2), float(eps), int(step), float(grad_scale), _stream()))

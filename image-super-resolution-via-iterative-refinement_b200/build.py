@@ -17,7 +17,7 @@ def _digest():
     h = hashlib.sha256()
     files = []
     for d, _dirs, names in os.walk(CSRC):
-        files += [os.path.join(d, n) for n in names if n.endswith((".cu", ".cuh", ".h"))]
+        files += [os.path.join(d, n) for n in names if n.endswith((".cu", ".cuh", ".h", ".inc"))]
     files.append(os.path.join(PKG, "..", "include", "sr3_b200.h"))
     for f in sorted(files):
         h.update(os.path.relpath(f, PKG).encode())

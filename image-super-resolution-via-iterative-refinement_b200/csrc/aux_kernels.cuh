@@ -26,6 +26,29 @@ __device__ __forceinline__ void store_operand4(__nv_bfloat16* base, long long o,
     if (lo_off) *reinterpret_cast<uint2*>(base + o + lo_off) = pack_bf16x4_residual(a, b, c, d);
 }
 
+// ------------------------------------------------------------------------------------------------ dropout (unet.py:86, block2 only)
+// keep-mask of element (b, c, pixel) of a [B][HW][C] tensor: either an injected mask (tests: the reference's own masks, uint8 NCHW) or
+// Philox4x32-10 keyed by (seed; vector index, layer).  Forward and backward evaluate the same function.
+struct DropSpec {
+    const unsigned char* mask;     // optional [B][C][HW] (1 = keep)
+    float p;                       // drop probability; 0 = no dropout
+    unsigned int layer;
+    unsigned long long seed;
+};
+__device__ __forceinline__ void drop_scale4(const DropSpec& d, int b, int c, int pix, int C, int HW, float (&s)[4]) {
+    const float keep_scale = 1.0f / (1.0f - d.p);
+    if (d.mask) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s[j] = d.mask[(static_cast<long long>(b) * C + c + j) * HW + pix] ? keep_scale : 0.f;
+        return;
+    }
+    const unsigned long long vec = (static_cast<unsigned long long>(b) * HW + pix) * (C >> 2) + (c >> 2);
+    uint32_t ctr[4] = {static_cast<uint32_t>(vec), static_cast<uint32_t>(vec >> 32), d.layer, 0x5d0u};
+    philox4x32_10(ctr, static_cast<uint32_t>(d.seed), static_cast<uint32_t>(d.seed >> 32));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s[j] = (static_cast<float>(ctr[j]) * 2.3283064365386963e-10f >= d.p) ? keep_scale : 0.f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // GroupNorm apply: a = [silu]( (x - mean_g) * rstd_g * gamma_c + beta_c ), x = concat(src0, src1) along channels.
 // Statistics come from the per-(image, channel) sums the producing GEMM epilogues accumulated.
@@ -41,6 +64,7 @@ struct PrepParams {
     __nv_bfloat16* out_raw;                 // optional bf16(x), same shape
     int B, items_per_image;                 // persistent step kernel: work items = B x items_per_image blocks of pix_per_block pixels
     int precise;                            // 1: operands are (hi | lo) pairs -- out rows are 2 (C0+C1) wide, low halves C0+C1 elements behind
+    const DropSpec* drop;                   // training-mode forward only: Dropout after the SiLU (unet.py:86); nullptr otherwise
 };
 
 // Per-(image, channel) scale / shift of a GroupNorm from the fp64 channel sums: y = x * sc[c] + sh[c].
@@ -137,6 +161,11 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
             if (pp < pix1) {
                 float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
                 if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+                if (p.drop != nullptr && p.drop->p > 0.f) {
+                    float ds[4];
+                    drop_scale4(*p.drop, b, c, pp, C, p.HW, ds);
+                    y0 *= ds[0]; y1 *= ds[1]; y2 *= ds[2]; y3 *= ds[3];
+                }
                 const long long o = (img + pp) * (p.precise ? 2 * C : C) + c;
                 const long long lo_off = p.precise ? C : 0;
                 store_operand4(p.out_a, o, lo_off, y0, y1, y2, y3);

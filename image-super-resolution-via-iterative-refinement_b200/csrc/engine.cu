@@ -20,6 +20,7 @@
 #include "aux_kernels.cuh"
 #include "attn_tcgen05.cuh"
 #include "step_megakernel.cuh"
+#include "train_kernels.cuh"
 
 using namespace sr3;
 typedef __nv_bfloat16 bf16;
@@ -650,6 +651,9 @@ void add_conv_slabs(std::vector<KSlab>& slabs, int a_sel, int cin, int ksize, in
 struct Act {
     float* p = nullptr; double* stats = nullptr;
     int C = 0, H = 0, W = 0;
+    // training plan only: gradient of the loss with respect to this tensor (fp32 NHWC), its bf16 copy (operand of the data / weight gradient
+    // GEMMs) and its per-(image, channel) sums (bias gradients), all complete when the producing layer's backward runs
+    float* g = nullptr; bf16* gb = nullptr; float* gsum = nullptr;
 };
 
 struct ParamEntry {
@@ -657,6 +661,7 @@ struct ParamEntry {
     std::vector<int64_t> shape;
     int64_t numel = 0;
     std::function<void(const float*, cudaStream_t)> load;
+    std::vector<std::function<void(const float*, cudaStream_t)>> hooks;   // training plan: further packed copies of the same tensor (data-gradient weights)
     bool loaded = false;
 };
 
@@ -680,6 +685,20 @@ struct sr3_engine {
     std::map<std::string, size_t> role_max;
     std::map<std::string, void*> role_ptr;
     bool dry = true;
+    // ---- training plan (sr3_engine_create_train): every scratch tensor of the forward is kept for the backward, which is recorded layer by
+    // layer while the forward plan is built and replayed in reverse order
+    bool train = false; float drop_p = 0.f;
+    std::vector<Op>* bwd_sink = nullptr;                   // where push() records while a layer's backward is being described
+    std::vector<std::vector<Op>> bwd_blocks;               // one op list per forward layer, executed last to first
+    std::vector<float*> grad_dst;                          // per parameter (state_dict order): where the running backward writes its gradient
+    float gscale = 1.f;                                    // d(total) / d(summed loss) of the running backward (1 / (b c h w), model.py:50-53)
+    float* zero_arena = nullptr; size_t zero_cap = 0, zero_used = 0;    // everything the backward accumulates into (cleared at its start)
+    DropSpec* drop_dev = nullptr; std::vector<DropSpec> drop_host; std::vector<std::string> drop_names;
+    bf16* last_xraw = nullptr;
+    bf16* deps_b = nullptr; float* fin_bias_sum = nullptr; float* dfilm = nullptr; float* dtau = nullptr;
+    float *dwf_all = nullptr, *dbf_all = nullptr, *dcb_all = nullptr;
+    float *hr_buf = nullptr;
+    int loss_type_cur = 1;
 
     StepCtl* ctl_dev = nullptr;
     StepCtl ctl{};
@@ -717,6 +736,11 @@ struct sr3_engine {
 
     // ---- buffers shared between layers of the same role (stream order makes reuse safe)
     void* role(const std::string& r, size_t bytes) {
+        // training plan: forward scratch is read again by the backward -> one allocation per use ("g_*" = backward scratch stays shared)
+        if (train && r.compare(0, 2, "g_") != 0) {
+            if (dry) return reinterpret_cast<void*>(0x1000);
+            return mem.alloc(bytes);
+        }
         if (dry) { size_t& m = role_max[r]; if (bytes > m) m = bytes; return reinterpret_cast<void*>(0x1000); }
         REQUIRE(role_ptr.count(r) && role_max[r] >= bytes, "role buffer %s too small", r.c_str());
         return role_ptr[r];
@@ -732,11 +756,29 @@ struct sr3_engine {
     Act new_act(int C, int Hh, int Ww, const std::string& tap_name = "") {
         Act a; a.C = C; a.H = Hh; a.W = Ww;
         a.stats = new_stats(C);
+        if (train) a.gsum = new_zero((size_t)Bp * C);
         if (!dry) {
             a.p = static_cast<float*>(mem.alloc((size_t)Bp * Hh * Ww * C * sizeof(float)));
+            if (train) {
+                a.g = static_cast<float*>(mem.alloc((size_t)Bp * Hh * Ww * C * sizeof(float)));
+                a.gb = static_cast<bf16*>(mem.alloc((size_t)Bp * Hh * Ww * C * sizeof(bf16)));
+            }
             if (!tap_name.empty()) taps[tap_name] = a;
         }
         return a;
+    }
+    // floats from the arena the backward clears before it starts (sums it accumulates into with atomics)
+    float* new_zero(size_t n) {
+        n = (n + 3) & ~size_t(3);
+        if (dry) { zero_used += n; return nullptr; }
+        REQUIRE(zero_used + n <= zero_cap, "zero arena overflow");
+        float* p = zero_arena + zero_used;
+        zero_used += n;
+        return p;
+    }
+    void add_param_hook(const std::string& name, std::function<void(const float*, cudaStream_t)> fn) {
+        if (dry) return;
+        params[pindex.at(name)].hooks.push_back(std::move(fn));
     }
     void add_param(const std::string& name, std::vector<int64_t> shape, std::function<void(const float*, cudaStream_t)> load) {
         if (dry) return;
@@ -783,6 +825,7 @@ struct sr3_engine {
     }
     void push(Op op, int kind = 4, double flops = 0, double bytes = 0) {
         if (dry) return;
+        if (bwd_sink) { bwd_sink->push_back(std::move(op)); return; }
         ops.push_back(std::move(op));
         op_info.push_back({kind, flops, bytes});
     }
@@ -802,9 +845,10 @@ struct sr3_engine {
     }
 
     // ---- layer builders -------------------------------------------------------------------------
-    void add_prep(const Act& s0, const Act* s1, const float* gamma, const float* beta, int groups, bool silu, bf16* out_a, bf16* out_raw) {
+    void add_prep(const Act& s0, const Act* s1, const float* gamma, const float* beta, int groups, bool silu, bf16* out_a, bf16* out_raw, const DropSpec* drop = nullptr) {
         if (dry) return;
         PrepParams p{};
+        p.drop = drop;
         p.src0 = s0.p; p.st0 = s0.stats; p.C0 = s0.C;
         p.src1 = s1 ? s1->p : nullptr; p.st1 = s1 ? s1->stats : nullptr; p.C1 = s1 ? s1->C : 0;
         p.gamma = gamma; p.beta = beta; p.groups = groups; p.HW = s0.H * s0.W; p.silu = silu ? 1 : 0; p.eps = 1e-5f;
@@ -879,7 +923,7 @@ struct sr3_engine {
     }
 
     // ResnetBlock (+ optional SelfAttention): reference unet.py:94-158
-    Act add_res_block(const LayerSpec& L, const Act& x, const Act* skip, int& film_off, bf16* raw_out = nullptr) {
+    Act add_res_block(const LayerSpec& L, const Act& x, const Act* skip, int& film_off, bf16* raw_out = nullptr, bool x_has_skip = false) {
         const int cin = x.C + (skip ? skip->C : 0), cout = L.cout, Hh = x.H, Ww = x.W, G = cfg.norm_groups;
         REQUIRE(cin == L.cin, "%s: cin mismatch %d vs %d", L.name.c_str(), cin, L.cin);
         const std::string p = L.name + ".res_block";
@@ -926,7 +970,16 @@ struct sr3_engine {
             c.out = h;
             add_conv(c);
         }
-        add_prep(h, nullptr, g2, b2, G, true, a2, nullptr);
+        const DropSpec* drop = nullptr;
+        if (train && drop_p > 0.f) {          // Dropout sits in block2 only (unet.py:100-101)
+            if (!dry) {
+                REQUIRE(drop_host.size() < 256, "too many dropout layers");
+                DropSpec ds{}; ds.mask = nullptr; ds.p = drop_p; ds.layer = (unsigned)drop_host.size(); ds.seed = 0;
+                drop = drop_dev + drop_host.size();
+                drop_host.push_back(ds); drop_names.push_back(p + ".block2");
+            }
+        }
+        add_prep(h, nullptr, g2, b2, G, true, a2, nullptr, drop);
         {
             ConvArgs c; c.n_a = has_res ? 2 : 1; c.a[0] = nhwc_src(a2, Bp, Hh, Ww, cout * PW); c.c0 = cout;
             add_conv_slabs(c.slabs, 0, cout, 3, 1, 0);
@@ -937,8 +990,13 @@ struct sr3_engine {
             if (!L.attn) c.raw_out = raw_out;
             add_conv(c);
         }
-        if (!L.attn) return y;
-        return add_attention(L, y, raw_out);
+        if (train) {
+            if (!dry) film_slices.push_back({foff, cout, pid(p + ".noise_func.noise_func.0.weight"), pid(p + ".noise_func.noise_func.0.bias"), pid(p + ".block1.block.3.bias")});
+            ResBwdCtx c; c.p = p; c.x = x; c.skip = skip; c.h = h; c.y = y; c.cin = cin; c.cout = cout; c.Hh = Hh; c.Ww = Ww; c.foff = foff;
+            c.has_res = has_res; c.x_acc = x_has_skip; c.a1 = a1; c.raw = raw; c.a2 = a2; c.g1 = g1; c.b1 = b1; c.g2 = g2; c.b2 = b2; c.drop = drop;
+            bwd_res_block(c);
+        }
+        return L.attn ? add_attention(L, y, raw_out) : y;      // (its backward is recorded after the block's: it runs first)
     }
 
     // SelfAttention (reference unet.py:113-142): GN -> qkv 1x1 (no bias) -> softmax(q k^T / sqrt(C)) v -> out 1x1 + bias + x
@@ -965,7 +1023,10 @@ struct sr3_engine {
         bf16* O = static_cast<bf16*>(role("O", (size_t)Bp * HW * C * 2 * PW));
         Act y = new_act(C, Hh, Ww, L.name);
         add_prep(x, nullptr, gn_w, gn_b, G, false, n, nullptr);
-        if (dry) return y;
+        if (dry) {
+            if (train) { AttnBwdCtx c; c.p = p; c.x = x; c.y = y; c.C = C; c.Hh = Hh; c.Ww = Ww; c.Lt = Lt; c.per = per; c.nz = nz; c.n = n; c.qk = qk; c.vT = vT; c.P = P; c.O = O; c.gn_w = gn_w; c.gn_b = gn_b; bwd_attention(c); }
+            return y;
+        }
         const bool merged_qkv = (getenv("SR3_NO_MERGED_QKV") == nullptr || precise) && C % 128 == 0;     // whole 128-column tiles on either side of 2C
         {   // q,k (,v) = Wqkv n : [Bp*HW tokens] x [2C (3C)]; the v columns are stored transposed as vT[z][d][token]
             GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(n, Bp, Hh, Ww, C * PW);
@@ -990,7 +1051,7 @@ struct sr3_engine {
             d.out_bf16 = vT; d.hs = OutSpec{(long long)C * Lt, 0, 0, Lt, 0};
             push_gemm(d);
         }
-        if (attn_fusable(Lt, C) && !precise) {
+        if (attn_fusable(Lt, C) && !precise && !train) {
             // S = q k^T / sqrt(C), softmax over the keys of the same image, O = P v: one launch (attn_tcgen05.cuh)
             const double fl = 4.0 * nz * (double)Lt * Lt * C;
             push(make_attn_op(qk, vT, O, nz, Lt, HW, C), 5, fl, (double)nz * Lt * C * 2 * 4);
@@ -1032,8 +1093,15 @@ struct sr3_engine {
             c.w = wout; c.ktot = C; c.cout = C; c.OH = Hh; c.OW = Ww; c.bias = bout; c.resid = x.p; c.out = y; c.raw_out = raw_out;
             add_conv(c);
         }
+        if (train) {
+            AttnBwdCtx c; c.p = p; c.x = x; c.y = y; c.C = C; c.Hh = Hh; c.Ww = Ww; c.Lt = Lt; c.per = per; c.nz = nz; c.n = n; c.qk = qk; c.vT = vT; c.P = P; c.O = O;
+            c.gn_w = gn_w; c.gn_b = gn_b;
+            bwd_attention(c);
+        }
         return y;
     }
+
+#include "train_plan.inc"
 
     void build_plan() {
         // topology: reference unet.py:186-231
@@ -1072,6 +1140,15 @@ struct sr3_engine {
         int min_res = cfg.image_size;
         for (int i = 1; i < cfg.n_mults; ++i) min_res /= 2;
         REQUIRE(min_res >= 8, "lowest UNet resolution %d < 8 is not supported", min_res);
+        if (train) {
+            fin_bias_sum = new_zero(4); dfilm = new_zero((size_t)Bp * F); dtau = new_zero((size_t)Bp * inner);
+            if (!dry) {
+                deps_b = static_cast<bf16*>(mem.alloc((size_t)Bp * H * W * 64 * sizeof(bf16)));
+                dwf_all = static_cast<float*>(mem.alloc((size_t)F * inner * 4)); dbf_all = static_cast<float*>(mem.alloc((size_t)F * 4));
+                dcb_all = static_cast<float*>(mem.alloc((size_t)F * 4));
+                drop_dev = static_cast<DropSpec*>(mem.alloc(256 * sizeof(DropSpec)));
+            }
+        }
 
         if (!dry) {
             mlp_w1 = f32_param("noise_level_mlp.1.weight", {4 * inner, inner});
@@ -1117,33 +1194,37 @@ struct sr3_engine {
                 add_conv_slabs(c.slabs, 0, in_C, 3, 1, 0);
                 c.w = w; c.ktot = 9 * in_C; c.cout = inner; c.OH = H; c.OW = W; c.bias = b; c.out = x;
                 add_conv(c);
+                if (train) bwd_first_conv(L.name, x);
                 if (!dry) side_join = (int)ops.size();      // the FiLM biases are first read by the next block's conv1 epilogue
             } else if (L.kind == 1) {
                 bf16* xr = (fuse_cast && next_is_down) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2 * PW)) : nullptr;
-                x = add_res_block(L, x, nullptr, film_off, xr);
+                last_xraw = xr;
+                x = add_res_block(L, x, nullptr, film_off, xr, /*x_has_skip=*/true);
             } else {                    // Downsample: conv3x3 stride 2 on the raw stream (unet.py:68-74)
                 const int C = x.C;
                 bf16* w = new_weight(C, 9 * C, pick_block_n(C));
                 conv_weight_param(L.name + ".conv.weight", w, C, C, 3, 9 * C, 0, C);
                 float* b = f32_param(L.name + ".conv.bias", {C});
-                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * x.H * x.W * C * 2 * PW));
+                bf16* raw = (train && fuse_cast) ? last_xraw : static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * x.H * x.W * C * 2 * PW));
                 if (!fuse_cast) add_cast(x, raw, 1);
                 Act y = new_act(C, x.H / 2, x.W / 2, L.name);
                 ConvArgs c; c.n_a = 1; c.a[0] = nhwc_stride2_src(raw, Bp, x.H, x.W, C * PW); c.c0 = C;
                 add_conv_slabs(c.slabs, 0, C, 3, 2, 0, C * PW);
                 c.w = w; c.ktot = 9 * C; c.cout = C; c.OH = y.H; c.OW = y.W; c.bias = b; c.out = y;
                 add_conv(c);
+                if (train) bwd_downsample(L.name, x, y, raw);
                 x = y;
             }
             feats.push_back(x);
         }
-        for (auto& L : mid) x = add_res_block(L, x, nullptr, film_off);
+        for (size_t mi = 0; mi < mid.size(); ++mi) x = add_res_block(mid[mi], x, nullptr, film_off, nullptr, /*x_has_skip=*/mi == 0);
         for (size_t li = 0; li < ups.size(); ++li) {
             auto& L = ups[li];
             const bool next_is_up = li + 1 < ups.size() && ups[li + 1].kind == 3;
             if (L.kind == 1) {
                 Act skip = feats.back(); feats.pop_back();
                 bf16* xr = (fuse_cast && fold_up && next_is_up) ? static_cast<bf16*>(role("xraw", (size_t)Bp * x.H * x.W * L.cout * 2 * PW)) : nullptr;
+                last_xraw = xr;
                 x = add_res_block(L, x, &skip, film_off, xr);
             } else if (!fold_up) {      // Upsample: nearest 2x then conv3x3 (unet.py:58-65), materialised
                 const int C = x.C;
@@ -1181,8 +1262,13 @@ struct sr3_engine {
                     });
                 }
                 float* b = f32_param(L.name + ".conv.bias", {C});
-                bf16* raw = static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2 * PW));
+                bf16* raw = (train && fuse_cast) ? last_xraw : static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2 * PW));
                 if (!fuse_cast) add_cast(x, raw, 1);
+                bf16* upb = nullptr;
+                if (train) {      // the weight gradient contracts dY with the nearest-2x upsampled input: keep a bf16 copy of it
+                    upb = static_cast<bf16*>(role("up_x", (size_t)Bp * Hl * 2 * Wl * 2 * C * 2));
+                    add_cast(x, upb, 2);
+                }
                 Act y = new_act(C, Hl * 2, Wl * 2, L.name);
                 for (int ph = 0; ph < (merge ? 1 : 4); ++ph) {
                     const int py = ph >> 1, px = ph & 1;
@@ -1199,6 +1285,7 @@ struct sr3_engine {
                     if (merge) { c.nz = 4; c.b_zrows = rows_pad; c.z_phase = 1; c.z_off_hi = 2LL * Wl * C; c.z_off_lo = C; }
                     add_conv(c);
                 }
+                if (train) bwd_upsample(L.name, x, y, upb);
                 x = y;
             }
         }
@@ -1213,6 +1300,7 @@ struct sr3_engine {
             float* b = f32_param("final_conv.block.3.bias", {co});
             bf16* a = static_cast<bf16*>(role("a1", (size_t)Bp * H * W * C * 2 * PW));
             add_prep(x, nullptr, g, be, cfg.norm_groups, true, a, nullptr);
+            if (train) bwd_final(x, a, g, be);
             if (!dry) {
                 GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C * PW);
                 add_conv_slabs(d.slabs, 0, C, 3, 1, 0);
@@ -1250,9 +1338,16 @@ struct sr3_engine {
         Bp = (B + 1) & ~1;                         // 8x8 levels tile two images per CTA
         use_graph = getenv("SR3_NO_GRAPH") == nullptr;
         T_cap = 4096;
+        REQUIRE(!(train && precise), "the training plan supports the bf16 precision only");
         // pass 1: sizes
-        dry = true; stats_used = 0;
+        dry = true; stats_used = 0; zero_used = 0;
         build_plan();
+        bwd_blocks.clear(); bwd_block_params.clear(); film_slices.clear(); drop_host.clear(); drop_names.clear();
+        if (train) {
+            zero_cap = zero_used + 4;
+            zero_arena = static_cast<float*>(mem.alloc(zero_cap * sizeof(float)));
+            loss_dev = static_cast<double*>(mem.alloc(sizeof(double)));
+        }
         // allocate
         stats_cap = (stats_used + 3) & ~size_t(3);
         stats_arena = static_cast<double*>(mem.alloc(stats_cap * sizeof(double)));
@@ -1267,13 +1362,13 @@ struct sr3_engine {
         nl_table = static_cast<float*>(mem.alloc((T_cap + 1) * 4));
         post_tab = static_cast<float*>(mem.alloc((size_t)5 * T_cap * 4));
         // pass 2: real plan
-        dry = false; stats_used = 0;
+        dry = false; stats_used = 0; zero_used = 0;
         g_gemm_registry = &gemms;
         g_mega_registry = &mega;
         try { build_plan(); } catch (...) { g_gemm_registry = nullptr; g_mega_registry = nullptr; throw; }
         g_gemm_registry = nullptr;
         g_mega_registry = nullptr;
-        if (getenv("SR3_NO_PREFETCH") == nullptr) {
+        if (getenv("SR3_NO_PREFETCH") == nullptr && !train) {
             // every tile kernel pulls the weights of the next one into L2 (the last one those of the next step's first)
             for (size_t i = 0; i < gemms.size(); ++i) {
                 const GemmHandle& nx = gemms[(i + 1) % gemms.size()];
@@ -1293,7 +1388,7 @@ struct sr3_engine {
         // Off by default: measured on the B200 (profiles/r02_step_kernel.md) the grid barrier + per-op fill / drain costs as much as a
         // launch inside a CUDA graph, and the 320-thread GroupNorm apply runs at half the bandwidth of the stand-alone kernel.
         // SR3_MEGA=1 selects it (bit-identical results).
-        use_mega = getenv("SR3_MEGA") != nullptr && atoi(getenv("SR3_MEGA")) != 0 && getenv("SR3_NO_FUSE_CAST") == nullptr && getenv("SR3_NO_FOLD_UP") == nullptr;
+        use_mega = !train && getenv("SR3_MEGA") != nullptr && atoi(getenv("SR3_MEGA")) != 0 && getenv("SR3_NO_FUSE_CAST") == nullptr && getenv("SR3_NO_FOLD_UP") == nullptr;
         if (!use_mega) return;
         std::vector<MegaOp> host_ops;
         std::vector<uint8_t> blob;
@@ -1403,7 +1498,7 @@ struct sr3_engine {
 extern "C" {
 
 const char* sr3_last_error(void) { return g_err.c_str(); }
-int sr3_abi_version(void) { return 2; }
+int sr3_abi_version(void) { return 3; }
 
 int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out) {
     API_BEGIN
@@ -1413,7 +1508,92 @@ int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_eng
     *out = e.release();
     API_END
 }
+int sr3_engine_create_train(const sr3_unet_config* cfg, int batch, int device, float dropout, sr3_engine** out) {
+    API_BEGIN
+    REQUIRE(cfg && out, "null argument");
+    REQUIRE(dropout >= 0.f && dropout < 1.f, "dropout %f out of range", dropout);
+    std::unique_ptr<sr3_engine> e(new sr3_engine());
+    e->train = true; e->drop_p = dropout;
+    e->init(*cfg, batch, device);
+    *out = e.release();
+    API_END
+}
 void sr3_engine_destroy(sr3_engine* e) { delete e; }
+
+int sr3_train_forward(sr3_engine* e, const float* hr, const float* sr, const float* gamma, const float* noise, int loss_type, uint64_t dropout_seed,
+                      double* loss_host, void* stream) {
+    API_BEGIN
+    REQUIRE(e && hr && gamma && noise, "null argument");
+    REQUIRE(loss_type == 1 || loss_type == 2, "loss_type must be 1 (l1) or 2 (l2)");
+    CK(cudaSetDevice(e->dev));
+    e->check_params();
+    e->train_forward(hr, sr, gamma, noise, loss_type, dropout_seed, loss_host, static_cast<cudaStream_t>(stream));
+    API_END
+}
+int sr3_train_backward(sr3_engine* e, float grad_scale, float* const* grads, int n_grads, void* stream) {
+    API_BEGIN
+    REQUIRE(e && grads, "null argument");
+    REQUIRE(n_grads == (int)e->params.size(), "expected %d gradient pointers, got %d", (int)e->params.size(), n_grads);
+    CK(cudaSetDevice(e->dev));
+    e->train_backward(grad_scale, grads, static_cast<cudaStream_t>(stream));
+    API_END
+}
+/* the same backward, layer by layer (last layer first), so that a caller can overlap the gradient all-reduce of finished layers */
+int sr3_train_num_backward_blocks(const sr3_engine* e) { return e ? (int)e->bwd_blocks.size() : 0; }
+int sr3_train_backward_begin(sr3_engine* e, float grad_scale, float* const* grads, int n_grads) {
+    API_BEGIN
+    REQUIRE(e && grads && n_grads == (int)e->params.size(), "bad argument");
+    e->train_backward_begin(grad_scale, grads);
+    API_END
+}
+int sr3_train_backward_block(sr3_engine* e, int block, void* stream) {
+    API_BEGIN
+    REQUIRE(e, "null engine");
+    CK(cudaSetDevice(e->dev));
+    e->train_backward_block(block, static_cast<cudaStream_t>(stream));
+    API_END
+}
+int sr3_train_backward_finish(sr3_engine* e, void* stream) {
+    API_BEGIN
+    REQUIRE(e && !e->grad_dst.empty(), "sr3_train_backward_begin has not been called");
+    CK(cudaSetDevice(e->dev));
+    e->bwd_film_and_embed(static_cast<cudaStream_t>(stream));
+    API_END
+}
+int sr3_train_block_params(const sr3_engine* e, int block, int* indices, int cap, int* n) {
+    API_BEGIN
+    REQUIRE(e && block >= 0 && block < (int)e->bwd_block_params.size() && n, "bad argument");
+    const std::vector<int>& v = e->bwd_block_params[block];
+    *n = (int)v.size();
+    for (int i = 0; i < (int)v.size() && i < cap; ++i) indices[i] = v[i];
+    API_END
+}
+int sr3_train_set_dropout_mask(sr3_engine* e, const char* block_name, const unsigned char* mask_nchw) {
+    API_BEGIN
+    REQUIRE(e && block_name, "null argument");
+    REQUIRE(e->train, "engine was not created with sr3_engine_create_train");
+    bool found = false;
+    for (size_t i = 0; i < e->drop_names.size(); ++i)
+        if (e->drop_names[i] == block_name) { e->drop_host[i].mask = mask_nchw; found = true; }
+    REQUIRE(found, "no dropout layer named %s", block_name);
+    API_END
+}
+int sr3_train_num_dropout_layers(const sr3_engine* e) { return e ? (int)e->drop_names.size() : 0; }
+int sr3_train_dropout_layer_name(const sr3_engine* e, int index, char* name, int name_cap) {
+    API_BEGIN
+    REQUIRE(e && index >= 0 && index < (int)e->drop_names.size() && name && name_cap > 0, "bad argument");
+    strncpy(name, e->drop_names[index].c_str(), name_cap - 1); name[name_cap - 1] = 0;
+    API_END
+}
+int sr3_adam_step(const void* table_dev, int n_tensors, float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream) {
+    API_BEGIN
+    REQUIRE(table_dev && n_tensors > 0 && step >= 1, "bad argument");
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    const int ny = n_tensors < 65535 ? n_tensors : 65535;
+    adam_kernel<<<dim3(64, ny), 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const AdamTensor*>(table_dev), n_tensors, lr, beta1, beta2, eps, bc1, sqrtf(bc2), grad_scale);
+    CK(cudaGetLastError());
+    API_END
+}
 
 int sr3_engine_num_params(const sr3_engine* e) { return e ? (int)e->params.size() : 0; }
 int sr3_engine_param_info(const sr3_engine* e, int index, char* name, int name_cap, int64_t shape[4], int* ndim) {
@@ -1434,6 +1614,7 @@ int sr3_engine_load_param(sr3_engine* e, const char* name, const float* src, int
     REQUIRE(p.numel == numel, "size mismatch for %s: expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
     CK(cudaSetDevice(e->dev));
     p.load(src, static_cast<cudaStream_t>(stream));
+    for (auto& h : p.hooks) h(src, static_cast<cudaStream_t>(stream));
     p.loaded = true;
     API_END
 }

@@ -42,6 +42,27 @@ _BUFFERS = ("betas", "alphas_cumprod", "alphas_cumprod_prev", "sqrt_alphas_cumpr
             "posterior_log_variance_clipped", "posterior_mean_coef1", "posterior_mean_coef2")
 
 
+class _PLossesFn(torch.autograd.Function):
+    """The native training forward / backward as one autograd node: forward = sr3_train_forward (q_sample, UNet in training mode, summed
+    loss), backward = sr3_train_backward (gradients of all parameters, in the reference's layouts).  reference: model.py:48-58."""
+
+    @staticmethod
+    def forward(ctx, module, eng, hr, sr, gamma, noise, seed, *params):
+        loss = eng.train_forward(hr, sr, gamma, noise, module.loss_type, seed)
+        ctx.eng = eng
+        ctx.names = [n for n, _ in eng.param_table()]
+        by_name = dict(module.denoise_fn.named_parameters())
+        ctx.order = [by_name[n] for n in ctx.names]
+        ctx.params = params
+        return torch.tensor(loss, dtype=torch.float32, device=hr.device)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = {id(p): torch.empty_like(p, memory_format=torch.contiguous_format) for p in ctx.order}
+        ctx.eng.train_backward(float(grad_out), [grads[id(p)] for p in ctx.order])
+        return (None,) * 7 + tuple(grads[id(p)] if p.requires_grad else None for p in ctx.params)
+
+
 class GaussianDiffusion(nn.Module):
     def __init__(self, denoise_fn, image_size, channels=3, loss_type="l1", conditional=True, schedule_opt=None):
         super().__init__()
@@ -132,27 +153,31 @@ class GaussianDiffusion(nn.Module):
         noise = torch.randn_like(x_start) if noise is None else noise
         return continuous_sqrt_alpha_cumprod * x_start + (1 - continuous_sqrt_alpha_cumprod ** 2).sqrt() * noise
 
-    def p_losses(self, x_in, noise=None):
-        """diffusion.py:221-246 (loss VALUE through the native UNet; the backward pass is the next milestone)."""
+    def p_losses(self, x_in, noise=None, gamma=None, dropout_seed=None):
+        """diffusion.py:221-246.  With autograd enabled and trainable parameters the value carries a grad_fn (the native backward,
+        csrc/train_plan.inc), so the reference's `l_pix.backward(); optG.step()` (model.py:48-58) works unchanged; in train() mode the
+        Dropout of every ResnetBlock's block2 (unet.py:86,100-101) is applied.  `gamma` / `dropout_seed` inject the random draws (tests)."""
         x_start = x_in["HR"]
         b = x_start.shape[0]
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.denoise_fn.parameters()):
-            # reference model.py:48-58 calls l_pix.backward() on this value; the native path has no backward yet -- say so HERE instead of
-            # letting autograd fail later with "element 0 of tensors does not require grad"
-            raise NotImplementedError(
-                "sr3_b200: p_losses / forward compute the loss VALUE only (no autograd graph, Dropout not applied): training "
-                "(optimize_parameters) is not implemented. Wrap the call in torch.no_grad() to evaluate the loss.")
-        if self.training and getattr(self.denoise_fn, "dropout", 0):
-            raise NotImplementedError("sr3_b200: training-mode Dropout (p=%g) is not implemented; call .eval() first" % self.denoise_fn.dropout)
-        t = np.random.randint(1, self.num_timesteps + 1)
-        gamma = torch.FloatTensor(np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1], self.sqrt_alphas_cumprod_prev[t], size=b)).to(x_start.device)
-        gamma = gamma.view(b, -1)
+        if gamma is None:
+            t = np.random.randint(1, self.num_timesteps + 1)
+            gamma = torch.FloatTensor(np.random.uniform(self.sqrt_alphas_cumprod_prev[t - 1], self.sqrt_alphas_cumprod_prev[t], size=b))
+        gamma = gamma.to(x_start.device).view(b, -1)
         noise = torch.randn_like(x_start) if noise is None else noise
         if self.loss_type not in ("l1", "l2"):
             raise NotImplementedError()
-        # q_sample + UNet + summed loss run in the native library (forward value; no autograd graph is attached)
-        val = self._engine(b).p_losses(x_start, x_in["SR"] if self.conditional else None, gamma.view(-1), noise, self.loss_type)
-        return torch.tensor(val, dtype=torch.float32, device=x_start.device)
+        sr = x_in["SR"] if self.conditional else None
+        params = [p for p in self.denoise_fn.parameters()]
+        needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        drop = float(getattr(self.denoise_fn, "dropout", 0) or 0) if self.training else 0.0
+        if not needs_grad and drop == 0.0:
+            # q_sample + UNet + summed loss on the inference plan (no intermediates kept)
+            val = self._engine(b).p_losses(x_start, sr, gamma.view(-1), noise, self.loss_type)
+            return torch.tensor(val, dtype=torch.float32, device=x_start.device)
+        if dropout_seed is None:
+            dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        eng = self.denoise_fn.engine(b, conditional=self.conditional, channels=self.channels, train_dropout=drop)
+        return _PLossesFn.apply(self, eng, x_start, sr, gamma.view(-1), noise, int(dropout_seed), *params)
 
     def forward(self, x, *args, **kwargs):
         return self.p_losses(x, *args, **kwargs)

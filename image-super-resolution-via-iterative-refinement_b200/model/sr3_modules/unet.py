@@ -179,16 +179,20 @@ class UNet(nn.Module):
         for eng in self._engines.values():
             eng.set_schedule(*self._schedule)
 
-    def engine(self, batch, conditional=True, channels=3):
+    def engine(self, batch, conditional=True, channels=3, train_dropout=None):
+        """train_dropout=None: the inference plan; a float: the TRAINING plan (intermediates kept, backward recorded) with that Dropout
+        probability -- see GaussianDiffusion.p_losses."""
         dev = next(self.parameters()).device
-        key = (batch, str(dev), bool(conditional), channels, self.precision)
+        key = (batch, str(dev), bool(conditional), channels, self.precision, train_dropout)
         eng = self._engines.pop(key, None)
         if eng is None:
             while len(self._engines) >= self.MAX_ENGINES:            # dicts keep insertion order: the first key is the least recently used
                 old = next(iter(self._engines))
                 del self._engines[old], self._engine_versions[old]
+            if train_dropout is not None and self.precision != "bf16":
+                raise NotImplementedError("sr3_b200: the training plan supports precision='bf16' only")
             cfg = dict(self.arch, channels=channels, conditional=conditional, precision=self.precision)
-            eng = _native.Engine(cfg, batch, dev)
+            eng = _native.Engine(cfg, batch, dev, train_dropout=train_dropout)
             self._engine_versions[key] = -1
             if self._schedule is not None:
                 eng.set_schedule(*self._schedule)

@@ -92,6 +92,39 @@ int sr3_p_sample(sr3_engine* e, const float* x, const float* condition_x, int t,
 int sr3_p_losses(sr3_engine* e, const float* hr, const float* sr, const float* gamma, const float* noise, int loss_type, double* loss_host,
                  void* stream);
 
+/* ---- training step: DDPM.optimize_parameters (model/model.py:48-58) = zero_grad -> GaussianDiffusion.forward / p_losses
+ * (diffusion.py:221-249) in train() mode -> l_pix.sum() / (b c h w) -> backward -> Adam step (model.py:39-40).
+ *
+ * sr3_engine_create_train: as sr3_engine_create, for a fixed batch, with a plan that keeps every intermediate of the forward and has the
+ * backward recorded next to it.  `dropout` = opt['model']['unet']['dropout'] (nn.Dropout in block2 of every ResnetBlock, unet.py:86,100-101);
+ * bf16 precision only.  Inference entry points keep working on such an engine (eval-mode semantics are NOT applied: use a plain engine). */
+int sr3_engine_create_train(const sr3_unet_config* cfg, int batch, int device, float dropout, sr3_engine** out);
+/* p_losses forward in training mode with the random draws injected (as sr3_p_losses): q_sample, UNet with Dropout (Philox keyed by
+ * dropout_seed, or the masks given to sr3_train_set_dropout_mask), summed L1 / L2 loss -> *loss_host (may be NULL: no synchronisation). */
+int sr3_train_forward(sr3_engine* e, const float* hr, const float* sr, const float* gamma, const float* noise, int loss_type, uint64_t dropout_seed,
+                      double* loss_host, void* stream);
+/* loss.backward() for the forward that just ran: grads[i] (DEVICE fp32, reference layout, one pointer per parameter in
+ * sr3_engine_param_info order, n_grads == sr3_engine_num_params) is OVERWRITTEN with grad_scale * d(summed loss)/d(parameter i)
+ * (grad_scale = 1 / (b c h w) reproduces model.py:50-53).  One backward per forward. */
+int sr3_train_backward(sr3_engine* e, float grad_scale, float* const* grads, int n_grads, void* stream);
+/* The same backward layer by layer, so that the caller can overlap the gradient all-reduce (training row) with the layers still to
+ * come: begin -> block n-1, n-2, ..., 0 -> finish (FiLM projections + noise-level MLP).  sr3_train_block_params lists the parameters whose
+ * gradient is final once `block` has run (the rest -- noise_func / block1 conv bias / noise_level_mlp -- are final after finish). */
+int sr3_train_num_backward_blocks(const sr3_engine* e);
+int sr3_train_backward_begin(sr3_engine* e, float grad_scale, float* const* grads, int n_grads);
+int sr3_train_backward_block(sr3_engine* e, int block, void* stream);
+int sr3_train_backward_finish(sr3_engine* e, void* stream);
+int sr3_train_block_params(const sr3_engine* e, int block, int* indices, int cap, int* n);
+/* Tests: replace the Philox dropout mask of ResnetBlock `block_name` ("downs.1.res_block.block2", the module that owns the nn.Dropout) by a
+ * keep-mask, uint8 DEVICE [B][C][H][W] (1 = keep), e.g. the one the reference drew; NULL restores Philox. */
+int sr3_train_set_dropout_mask(sr3_engine* e, const char* block_name, const unsigned char* mask_nchw);
+int sr3_train_num_dropout_layers(const sr3_engine* e);
+int sr3_train_dropout_layer_name(const sr3_engine* e, int index, char* name, int name_cap);
+/* torch.optim.Adam(lr, betas, eps, weight_decay 0) step `step` (1-based) over a DEVICE table of n_tensors records
+ * {float* param; const float* grad; float* exp_avg; float* exp_avg_sq; int64 numel} (40 bytes each) in ONE launch; gradients are multiplied by
+ * grad_scale first (1 / world_size after a summing all-reduce). */
+int sr3_adam_step(const void* table_dev, int n_tensors, float lr, float beta1, float beta2, float eps, int step, float grad_scale, void* stream);
+
 /* p_sample_loop / super_resolution / sample (diffusion.py:176-210): runs t = T-1 .. 0 as T launches of one captured CUDA
  * graph.  x_T: DEVICE [B,3,H,W] initial noise (the reference's torch.randn(shape)).  noises: optional DEVICE
  * [T][B,3,H,W], noises[i] used at step i.  Every (i % (1|T/10) == 0) the image is appended to `snapshots`
