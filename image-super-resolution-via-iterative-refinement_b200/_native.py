@@ -37,6 +37,7 @@ _SIGS = {
     "sr3_train_backward_block": (c_int, [c_void_p, c_int, c_void_p]),
     "sr3_train_backward_finish": (c_int, [c_void_p, c_void_p]),
     "sr3_train_block_params": (c_int, [c_void_p, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
+    "sr3_train_backward_profile": (c_int, [c_void_p, c_float, POINTER(c_void_p), c_int, POINTER(c_float), c_void_p]),
     "sr3_train_set_dropout_mask": (c_int, [c_void_p, c_char_p, c_void_p]),
     "sr3_train_num_dropout_layers": (c_int, [c_void_p]),
     "sr3_train_dropout_layer_name": (c_int, [c_void_p, c_int, c_char_p, c_int]),
@@ -45,6 +46,7 @@ _SIGS = {
     "sr3_engine_num_params": (c_int, [c_void_p]),
     "sr3_engine_param_info": (c_int, [c_void_p, c_int, c_char_p, c_int, POINTER(c_int64), POINTER(c_int)]),
     "sr3_engine_load_param": (c_int, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "sr3_engine_load_all_params": (c_int, [c_void_p, POINTER(c_void_p), c_int, c_void_p]),
     "sr3_engine_finalize_params": (c_int, [c_void_p, c_void_p]),
     "sr3_engine_set_schedule": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sr3_unet_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -180,6 +182,17 @@ class Engine:
             out.append((buf.value.decode(), tuple(shape[j] for j in range(nd.value))))
         return out
 
+    def load_params_fast(self, tensors):
+        """One native call for the whole parameter set (fp32 contiguous CUDA tensors in param_table() order), no synchronisation: the
+        training loop's re-pack after every optimizer step."""
+        arr = (c_void_p * len(tensors))()
+        for i, t in enumerate(tensors):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+                raise RuntimeError("load_params_fast needs contiguous fp32 CUDA tensors")
+            arr[i] = t.data_ptr()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_engine_load_all_params(self._h, arr, len(tensors), _stream()))
+
     def load_state_dict(self, sd: dict):
         keep = []
         with torch.cuda.device(self.device):
@@ -269,6 +282,15 @@ class Engine:
         arr = self._grad_ptrs(grads)
         with torch.cuda.device(self.device):
             _check(lib().sr3_train_backward(self._h, float(grad_scale), arr, len(grads), _stream()))
+
+    def train_backward_profile(self, grad_scale, grads):
+        """{kind: ms} of one backward, CUDA events around every op."""
+        arr = self._grad_ptrs(grads)
+        ms = (c_float * 8)()
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_backward_profile(self._h, float(grad_scale), arr, len(grads), ms, _stream()))
+        names = {0: "dgrad_tile_kernel", 1: "groupnorm_elementwise", 4: "other", 6: "wgrad", 7: "attention_gemms"}
+        return {names.get(k, str(k)): ms[k] for k in range(8) if ms[k] > 0}
 
     def num_backward_blocks(self):
         return lib().sr3_train_num_backward_blocks(self._h)

@@ -690,6 +690,7 @@ struct sr3_engine {
     bool train = false; float drop_p = 0.f;
     std::vector<Op>* bwd_sink = nullptr;                   // where push() records while a layer's backward is being described
     std::vector<std::vector<Op>> bwd_blocks;               // one op list per forward layer, executed last to first
+    std::vector<std::vector<int>> bwd_kinds;               // op kinds (profiling): 0 data-gradient tile kernel, 1 GroupNorm / elementwise, 4 other, 6 weight gradient, 7 attention GEMMs
     std::vector<float*> grad_dst;                          // per parameter (state_dict order): where the running backward writes its gradient
     float gscale = 1.f;                                    // d(total) / d(summed loss) of the running backward (1 / (b c h w), model.py:50-53)
     float* zero_arena = nullptr; size_t zero_cap = 0, zero_used = 0;    // everything the backward accumulates into (cleared at its start)
@@ -825,7 +826,7 @@ struct sr3_engine {
     }
     void push(Op op, int kind = 4, double flops = 0, double bytes = 0) {
         if (dry) return;
-        if (bwd_sink) { bwd_sink->push_back(std::move(op)); return; }
+        if (bwd_sink) { bwd_sink->push_back(std::move(op)); bwd_kinds.back().push_back(kind); return; }
         ops.push_back(std::move(op));
         op_info.push_back({kind, flops, bytes});
     }
@@ -1342,7 +1343,7 @@ struct sr3_engine {
         // pass 1: sizes
         dry = true; stats_used = 0; zero_used = 0;
         build_plan();
-        bwd_blocks.clear(); bwd_block_params.clear(); film_slices.clear(); drop_host.clear(); drop_names.clear();
+        bwd_blocks.clear(); bwd_kinds.clear(); bwd_block_params.clear(); film_slices.clear(); drop_host.clear(); drop_names.clear();
         if (train) {
             zero_cap = zero_used + 4;
             zero_arena = static_cast<float*>(mem.alloc(zero_cap * sizeof(float)));
@@ -1568,6 +1569,31 @@ int sr3_train_block_params(const sr3_engine* e, int block, int* indices, int cap
     for (int i = 0; i < (int)v.size() && i < cap; ++i) indices[i] = v[i];
     API_END
 }
+/* Profiling: the backward of the forward that just ran, with CUDA events around every op; ms_by_kind[8] receives the summed device time per
+ * op kind (0 data-gradient tile kernel, 1 GroupNorm / elementwise, 4 other, 6 weight gradient + slice reduction, 7 attention GEMMs). */
+int sr3_train_backward_profile(sr3_engine* e, float grad_scale, float* const* grads, int n_grads, float* ms_by_kind, void* stream) {
+    API_BEGIN
+    REQUIRE(e && grads && ms_by_kind && n_grads == (int)e->params.size(), "bad argument");
+    CK(cudaSetDevice(e->dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    e->train_backward_begin(grad_scale, grads);
+    std::vector<cudaEvent_t> evs;
+    std::vector<int> kinds;
+    auto mark = [&]() { cudaEvent_t ev; CK(cudaEventCreate(&ev)); CK(cudaEventRecord(ev, st)); evs.push_back(ev); };
+    mark();
+    for (size_t i = e->bwd_blocks.size(); i-- > 0;)
+        for (size_t j = 0; j < e->bwd_blocks[i].size(); ++j) { e->bwd_blocks[i][j](st); kinds.push_back(e->bwd_kinds[i][j]); mark(); }
+    e->bwd_film_and_embed(st); kinds.push_back(4); mark();
+    CK(cudaStreamSynchronize(st));
+    for (int k = 0; k < 8; ++k) ms_by_kind[k] = 0.f;
+    for (size_t i = 0; i < kinds.size(); ++i) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+        ms_by_kind[kinds[i] & 7] += ms;
+    }
+    for (auto ev : evs) cudaEventDestroy(ev);
+    API_END
+}
 int sr3_train_set_dropout_mask(sr3_engine* e, const char* block_name, const unsigned char* mask_nchw) {
     API_BEGIN
     REQUIRE(e && block_name, "null argument");
@@ -1616,6 +1642,23 @@ int sr3_engine_load_param(sr3_engine* e, const char* name, const float* src, int
     p.load(src, static_cast<cudaStream_t>(stream));
     for (auto& h : p.hooks) h(src, static_cast<cudaStream_t>(stream));
     p.loaded = true;
+    API_END
+}
+/* load_state_dict in one call: srcs[i] = DEVICE fp32 pointer of parameter i (sr3_engine_param_info order); re-packs everything and runs the
+ * finalisation.  Asynchronous on `stream` (the training loop calls it after every optimizer step). */
+int sr3_engine_load_all_params(sr3_engine* e, const float* const* srcs, int n, void* stream) {
+    API_BEGIN
+    REQUIRE(e && srcs && n == (int)e->params.size(), "expected %d parameter pointers", e ? (int)e->params.size() : 0);
+    CK(cudaSetDevice(e->dev));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < n; ++i) {
+        REQUIRE(srcs[i] != nullptr, "null pointer for %s", e->params[i].name.c_str());
+        ParamEntry& p = e->params[i];
+        p.load(srcs[i], st);
+        for (auto& h : p.hooks) h(srcs[i], st);
+        p.loaded = true;
+    }
+    for (auto& op : e->finalize_ops) op(st);
     API_END
 }
 int sr3_engine_finalize_params(sr3_engine* e, void* stream) {

@@ -199,7 +199,14 @@ class UNet(nn.Module):
         self._engines[key] = eng                                     # (re-)insert as most recently used
         ver = self._weights_version()
         if self._engine_versions[key] != ver:
-            eng.load_state_dict(self.state_dict())
+            order = getattr(eng, "_param_order", None)
+            if order is None:
+                by_name = dict(self.named_parameters())
+                order = eng._param_order = [by_name[n] for n, _ in eng.param_table()]
+            if all(p.is_cuda and p.dtype == torch.float32 and p.is_contiguous() and p.device == dev for p in order):
+                eng.load_params_fast([p.detach() for p in order])      # one native call, asynchronous (the per-step path of training)
+            else:
+                eng.load_state_dict(self.state_dict())
             self._engine_versions[key] = ver
         return eng
 

@@ -4,6 +4,11 @@ all-gather.  The reference only offers nn.DataParallel for traini
 (model/model.py:60-78); this is the B200-native replacement for that path: one process per GPU, NCCL over NVLink.
 
 Noise comes from Philox streams keyed by the GLOBAL sample index, so the result does not depend on the number of ranks.
+
+Training is plain data parallelism with ONE exchange step: every rank runs forward / backward on its slice of the
+batch, the parameter gradients are summed with NCCL all-reduces in buckets that are issued while the backward of the earlier layers is still
+running (the native backward is replayed layer by layer: sr3_train_backward_block), and Adam is applied redundantly on every rank.  The
+reference's own multi-GPU training is nn.DataParallel (model/networks.py:113-115: replicate + scatter + gather every forward).
 """
 from typing import Callable, Optional, Tuple
 
@@ -72,3 +77,156 @@ def sharded_super_resolution(netG, x_in: torch.Tensor, x_T: Optional[torch.Tenso
         return final
 
     return sharded_sample(fn, x_in, x_T, group)
+
+
+# ---------------------------------------------------------------------------------------------------------------- training
+def plan_buckets(block_param_indices, param_numels, bucket_elems):
+    """Group the backward's layers (last layer first) into gradient buckets of about `bucket_elems` elements.
+
+    block_param_indices[i] = parameter indices whose gradient is final once backward block i has run (blocks run n-1 .. 0); parameters that
+    appear in no block (FiLM projections, noise-level MLP: final only after the whole backward) form the last bucket.  Returns
+    [(first_block_done, [param indices])]: the bucket may be reduced as soon as block `first_block_done` has run (-1: after finish)."""
+    n_blocks = len(block_param_indices)
+    seen = set()
+    buckets, cur, cur_n = [], [], 0
+    for i in range(n_blocks - 1, -1, -1):
+        for pi in block_param_indices[i]:
+            if pi in seen:
+                continue
+            seen.add(pi)
+            cur.append(pi)
+            cur_n += param_numels[pi]
+        if cur_n >= bucket_elems:
+            buckets.append((i, cur))
+            cur, cur_n = [], 0
+    rest = [pi for pi in range(len(param_numels)) if pi not in seen]
+    if cur:
+        buckets.append((0, cur))
+    if rest:
+        buckets.append((-1, rest))
+    return buckets
+
+
+class GradientBuckets:
+    """Flat fp32 gradient arena cut into buckets in the order the backward finishes them; parameter i's gradient is the view `views[i]`.
+    ready(block) all-reduces (sum) every bucket that became final with backward block `block` -- on CUDA on a side stream, ordered behind the
+    work queued on the current stream so far, so the transfer overlaps the layers still to run; finish() joins the streams."""
+
+    def __init__(self, params, block_param_indices, bucket_elems, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        numels = [p.numel() for p in params]
+        self.buckets = plan_buckets(block_param_indices, numels, bucket_elems)
+        dev = params[0].device
+        self.flat = torch.zeros(sum(numels), dtype=torch.float32, device=dev)
+        self.views = [None] * len(params)
+        self.slices = []
+        off = 0
+        for first_block, idxs in self.buckets:
+            lo = off
+            for pi in idxs:
+                self.views[pi] = self.flat[off:off + numels[pi]].view(params[pi].shape)
+                off += numels[pi]
+            self.slices.append((first_block, lo, off))
+        assert off == self.flat.numel()
+        self.cuda = dev.type == "cuda"
+        self.comm_stream = torch.cuda.Stream(device=dev) if (self.cuda and self.world > 1) else None
+        self.pending = []
+        self.n_reduced = 0
+        self._t0 = self._t1 = None
+
+    def begin(self):
+        self.pending = list(self.slices)
+        self.n_reduced = 0
+        if self.comm_stream is not None:
+            self._t0, self._t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def ready(self, block):
+        while self.pending and self.pending[0][0] == block:
+            _, lo, hi = self.pending.pop(0)
+            self.n_reduced += 1
+            if self.world == 1:
+                continue
+            if self.comm_stream is None:
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                continue
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream())
+            self.comm_stream.wait_event(done)
+            with torch.cuda.stream(self.comm_stream):
+                if self.n_reduced == 1:
+                    self._t0.record(self.comm_stream)
+                dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+
+    def finish(self):
+        self.ready(-1)
+        assert not self.pending, "backward blocks were skipped"
+        if self.comm_stream is not None:
+            self._t1.record(self.comm_stream)
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def comm_window_ms(self):
+        """Device time from the start of the first to the end of the last all-reduce of the most recent step (overlapping the backward)."""
+        if self.comm_stream is None or self._t0 is None:
+            return 0.0
+        torch.cuda.synchronize()
+        return self._t0.elapsed_time(self._t1)
+
+
+class DataParallelTrainer:
+    """One process per GPU.  step(hr, sr) = DDPM.optimize_parameters (model/model.py:48-58) on this rank's slice of the global batch:
+    native forward -> native backward replayed layer by layer, each finished bucket of gradients all-reduced (sum) on a side stream while the
+    remaining layers run -> one fused Adam launch (gradients are scaled by 1 / (global b c h w) when they are produced, so the all-reduced
+    sum IS the gradient of the global mean the reference optimises).  Without a process group (world size 1) the collectives are skipped."""
+
+    def __init__(self, netG, lr=1e-4, bucket_mb=64.0, group=None):
+        from .optim import FusedAdam
+        self.net = netG
+        self.group = group
+        self.opt = FusedAdam(list(netG.denoise_fn.parameters()), lr=lr)
+        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
+        self._eng = None
+        self.buckets = None
+
+    def _prepare(self, eng):
+        if self._eng is eng:
+            return
+        by_name = dict(self.net.denoise_fn.named_parameters())
+        params = [by_name[n] for n, _ in eng.param_table()]
+        blocks = [eng.block_params(i) for i in range(eng.num_backward_blocks())]
+        self.buckets = GradientBuckets(params, blocks, self.bucket_elems, self.group)
+        for p, v in zip(params, self.buckets.views):
+            p.grad = v                           # the optimizer reads the all-reduced arena directly
+        self._eng = eng
+
+    def step(self, hr, sr, gamma=None, noise=None, dropout_seed=None, global_batch=None):
+        """hr / sr: THIS rank's slice [b,3,H,W] (device or host).  Returns the summed loss of the slice (python float)."""
+        import numpy as np
+        net = self.net
+        b, c, h, w = hr.shape
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        gb = global_batch if global_batch is not None else b * world
+        drop = float(getattr(net.denoise_fn, "dropout", 0) or 0) if net.training else 0.0
+        eng = net.denoise_fn.engine(b, conditional=net.conditional, channels=net.channels, train_dropout=drop)
+        self._prepare(eng)
+        if gamma is None:
+            t = np.random.randint(1, net.num_timesteps + 1)
+            gamma = torch.FloatTensor(np.random.uniform(net.sqrt_alphas_cumprod_prev[t - 1], net.sqrt_alphas_cumprod_prev[t], size=b))
+        if noise is None:
+            noise = torch.randn(hr.shape, device=net.betas.device)
+        if dropout_seed is None:
+            dropout_seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        loss = eng.train_forward(hr, sr if net.conditional else None, gamma, noise, net.loss_type, dropout_seed)
+        bk = self.buckets
+        eng.backward_begin(1.0 / float(gb * c * h * w), bk.views)
+        bk.begin()
+        for i in range(eng.num_backward_blocks() - 1, -1, -1):
+            eng.backward_block(i)
+            bk.ready(i)
+        eng.backward_finish()
+        bk.finish()
+        self.opt.step()
+        return loss
+
+    def comm_window_ms(self):
+        return self.buckets.comm_window_ms() if self.buckets is not None else 0.0

@@ -62,6 +62,9 @@ int sr3_engine_param_info(const sr3_engine* e, int index, char* name, int name_c
 /* load_state_dict for one tensor (model/model.py:146-160): `src` is a DEVICE fp32 pointer in the reference layout.
  * Weights are re-packed (OIHW -> K-major bf16) by a kernel on `stream`. */
 int sr3_engine_load_param(sr3_engine* e, const char* name, const float* src, int64_t numel, void* stream);
+/* The whole state_dict in one call (srcs[i] = DEVICE fp32 pointer of parameter i in sr3_engine_param_info order) including the finalisation;
+ * asynchronous on `stream`.  What the training loop calls after every optimizer step (model/model.py:58). */
+int sr3_engine_load_all_params(sr3_engine* e, const float* const* srcs, int n, void* stream);
 /* Must be called after the last load_param of a batch of updates (fuses bias vectors). */
 int sr3_engine_finalize_params(sr3_engine* e, void* stream);
 
@@ -115,6 +118,9 @@ int sr3_train_backward_begin(sr3_engine* e, float grad_scale, float* const* grad
 int sr3_train_backward_block(sr3_engine* e, int block, void* stream);
 int sr3_train_backward_finish(sr3_engine* e, void* stream);
 int sr3_train_block_params(const sr3_engine* e, int block, int* indices, int cap, int* n);
+/* Profiling: the whole backward with CUDA events around every op; ms_by_kind[8]: device time per op kind (0 data-gradient tile kernel,
+ * 1 GroupNorm / elementwise, 4 other, 6 weight gradient + slice reduction, 7 attention GEMMs). */
+int sr3_train_backward_profile(sr3_engine* e, float grad_scale, float* const* grads, int n_grads, float* ms_by_kind, void* stream);
 /* Tests: replace the Philox dropout mask of ResnetBlock `block_name` ("downs.1.res_block.block2", the module that owns the nn.Dropout) by a
  * keep-mask, uint8 DEVICE [B][C][H][W] (1 = keep), e.g. the one the reference drew; NULL restores Philox. */
 int sr3_train_set_dropout_mask(sr3_engine* e, const char* block_name, const unsigned char* mask_nchw);

@@ -83,3 +83,71 @@ def test_two_rank_sampling_matches_single_process(n, tmp_path):
     whole, _ = net._engine(n).p_sample_loop(cond.cuda(), xT.cuda(), None, 9, 0, want_snapshots=False)
     rel = ((whole.cpu() - outs[0]).norm() / outs[0].norm()).item()
     assert rel < 1e-2, rel
+
+
+# ---- training (config 4: data-parallel fwd + bwd + Adam, gradient all-reduce overlapped with the backward) -------------------------
+def _train_inputs(n):
+    g = torch.Generator().manual_seed(33)
+    hr = torch.rand(n, 3, 32, 32, generator=g) * 2 - 1
+    sr = torch.rand(n, 3, 32, 32, generator=g) * 2 - 1
+    noise = torch.randn(n, 3, 32, 32, generator=g)
+    gamma = torch.rand(n, generator=g) * 0.5 + 0.3
+    return hr, sr, noise, gamma
+
+
+def _build_train(dev):
+    import sr3_b200
+    torch.manual_seed(0)
+    o = _opt(); o["phase"] = "train"
+    net = sr3_b200.define_G(o).to(dev)
+    net.loss_type = "l2"                       # smooth loss: the comparison below is not blurred by sign flips of the L1 gradient
+    net.set_loss(dev)
+    net.set_new_noise_schedule(SCHED, dev)
+    net.eval()                                 # no Dropout: both runs see the same network
+    return net
+
+
+def _train_worker(rank, world, port, n, path):
+    import torch.distributed as dist
+    from sr3_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        net = _build_train(dev)
+        hr, sr, noise, gamma = _train_inputs(n)
+        lo, hi = parallel.shard_bounds(n, world, rank)
+        tr = parallel.DataParallelTrainer(net, lr=1e-4, bucket_mb=0.25)          # small buckets: several all-reduces in flight
+        loss = tr.step(hr[lo:hi].to(dev), sr[lo:hi].to(dev), gamma=gamma[lo:hi], noise=noise[lo:hi].to(dev), global_batch=n)
+        torch.cuda.synchronize()
+        torch.save({"loss": loss, "grad": tr.buckets.flat.cpu(), "n_buckets": len(tr.buckets.slices), "comm_ms": tr.comm_window_ms(),
+                    "params": {k: v.cpu() for k, v in net.denoise_fn.state_dict().items()}}, f"{path}.rank{rank}")
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_training_step_matches_single_process(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from sr3_b200 import parallel
+    n = 4
+    path = str(tmp_path / "tr")
+    mp.spawn(_train_worker, args=(2, _free_port(), n, path), nprocs=2, join=True)
+    outs = [torch.load(f"{path}.rank{r}") for r in range(2)]
+    assert outs[0]["n_buckets"] >= 3
+    assert torch.equal(outs[0]["grad"], outs[1]["grad"])                       # the all-reduced gradient is the same on both ranks
+    for k in outs[0]["params"]:
+        assert torch.equal(outs[0]["params"][k], outs[1]["params"][k]), k      # ... and so are the parameters after Adam
+    # one process, whole batch
+    net = _build_train(torch.device("cuda", 0))
+    hr, sr, noise, gamma = _train_inputs(n)
+    tr = parallel.DataParallelTrainer(net, lr=1e-4, bucket_mb=0.25)
+    loss = tr.step(hr.cuda(), sr.cuda(), gamma=gamma, noise=noise.cuda(), global_batch=n)
+    torch.cuda.synchronize()
+    assert abs((outs[0]["loss"] + outs[1]["loss"]) - loss) < 1e-3 * abs(loss)
+    g1, g2 = tr.buckets.flat.cpu(), outs[0]["grad"]
+    assert ((g1 - g2).norm() / g1.norm()).item() < 1e-2

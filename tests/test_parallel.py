@@ -102,3 +102,48 @@ def test_sharded_super_resolution_two_ranks_gloo(n):
         ret = m.dict()
         mp.spawn(_worker_sr, args=(world, port, n, ret), nprocs=world, join=True)
         assert dict(ret) == {0: True, 1: True}
+
+
+# ---- training: bucketed gradient all-reduce (training row) ------------------------------------------------------
+def test_plan_buckets_orders_by_backward_completion():
+    # 4 backward blocks (run 3, 2, 1, 0); parameter 6 belongs to no block (FiLM / noise MLP: final after the whole backward)
+    blocks = [[0, 1], [2], [3, 4], [5]]
+    numels = [10, 10, 10, 10, 10, 30, 7]
+    b = parallel.plan_buckets(blocks, numels, 25)
+    assert b == [(3, [5]), (1, [3, 4, 2]), (0, [0, 1]), (-1, [6])]
+    assert sorted(sum((ix for _, ix in b), [])) == list(range(7))
+    # one huge bucket: everything except the late parameters is reduced when block 0 has run
+    assert parallel.plan_buckets(blocks, numels, 10 ** 9) == [(0, [5, 3, 4, 2, 0, 1]), (-1, [6])]
+
+
+def _bucket_worker(rank, world, port, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        shapes = [(4, 3), (5,), (2, 2, 2), (7,), (3, 3), (6,), (2,)]
+        params = [torch.zeros(s) for s in shapes]
+        blocks = [[0, 1], [2], [3, 4], [5]]
+        gb = parallel.GradientBuckets(params, blocks, 12)
+        gb.begin()
+        for i in range(len(blocks) - 1, -1, -1):          # the "backward": block i writes its parameters' gradients, then reports
+            for pi in blocks[i]:
+                gb.views[pi].copy_(torch.full(shapes[pi], float((rank + 1) * (pi + 1))))
+            gb.ready(i)
+        gb.views[6].copy_(torch.full(shapes[6], float((rank + 1) * 7)))
+        gb.finish()
+        ok = gb.n_reduced == len(gb.slices)
+        for pi in range(7):
+            ok = ok and bool(torch.equal(gb.views[pi], torch.full(shapes[pi], float(3 * (pi + 1)))))     # (1 + 2) * (pi + 1)
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_buckets_two_ranks_gloo():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        ret = m.dict()
+        mp.spawn(_bucket_worker, args=(world, port, ret), nprocs=world, join=True)
+        assert dict(ret) == {0: True, 1: True}

@@ -109,3 +109,37 @@ def test_reference_ddpm_wrapper_samples_on_the_gpu(ref_model_pkg, tmp_path):
     # imports cv2, which this image does not have
     img = ((last.clamp(-1, 1) + 1) / 2 * 255.0).round().permute(1, 2, 0).numpy().astype(np.uint8)
     assert img.shape == (32, 32, 3) and img.dtype == np.uint8
+
+
+@pytest.mark.gpu
+def test_reference_optimize_parameters_trains_on_the_gpu(ref_model_pkg, tmp_path):
+    """model/model.py:48-58 UNMODIFIED (zero_grad -> netG(data) -> sum / (b c h w) -> backward -> torch.optim.Adam.step) over
+    sr3_b200.define_G: the loss carries our native backward as its grad_fn, every parameter receives a gradient, the parameters move and the
+    loss of a fixed batch goes down over a few iterations."""
+    ref_model, ref_networks, _ = ref_model_pkg
+    import numpy as np
+    opt = make_opt("train", str(tmp_path))
+    opt["gpu_ids"] = [0]
+    opt["model"]["unet"]["dropout"] = 0.2
+    torch.manual_seed(0)
+    np.random.seed(0)
+    m = ref_model.create_model(opt)
+    assert m.device.type == "cuda" and m.netG.training
+    before = {k: v.detach().clone() for k, v in m.netG.state_dict().items() if k.startswith("denoise_fn.")}
+    g = torch.Generator().manual_seed(3)
+    losses = []
+    for it in range(6):
+        data = {"HR": torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(3)) * 2 - 1,
+                "SR": torch.rand(2, 3, 32, 32, generator=torch.Generator().manual_seed(4)) * 2 - 1, "Index": torch.arange(2)}
+        m.feed_data(data)
+        np.random.seed(1)                          # the same (t, gamma) draw every iteration: the loss of this batch must go down
+        torch.manual_seed(1)
+        m.optimize_parameters()
+        losses.append(m.get_current_log()["l_pix"])
+        if it == 0:
+            missing = [k for k, p in m.netG.named_parameters() if p.grad is None or not torch.isfinite(p.grad).all() or p.grad.abs().sum() == 0]
+            assert not missing, missing[:5]
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+    moved = sum(int(not torch.equal(before[k], v)) for k, v in m.netG.state_dict().items() if k in before)
+    assert moved == len(before)
