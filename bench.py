@@ -294,7 +294,120 @@ def secondary_workloads(dev, peaks, steps=10):
         torch.cuda.empty_cache()
     except Exception as e:
         out["sr_16_128_b16_precise_fp32"] = {"error": f"{type(e).__name__}: {e}"}
+    # configs[3]: the training step, one GPU's share (8 images) of the global batch of 64
+    try:
+        ms, _, losses, n_blocks, _ = time_training(dev, 8, 8, 5, 3, torch.cuda.synchronize, None)
+        fl = 3.0 * algorithmic_flops_per_image() * 8
+        out["train_16_128_b8"] = {"config": "sr_sr3_16_128.json training step (fwd + bwd + Adam), 8 images (one GPU's share of batch 64)", "batch": 8,
+                                  "ms_per_step": ms, "steps_per_s": 1e3 / ms, "algorithmic_tflop_per_step": fl / 1e12, "achieved_tflops": fl / (ms * 1e-3) / 1e12,
+                                  "frac_of_measured_burst_bf16": fl / (ms * 1e-3) / 1e12 / peaks["burst"], "backward_blocks": n_blocks,
+                                  "loss_first_last": [losses[0], losses[-1]]}
+    except Exception as e:
+        out["train_16_128_b8"] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def time_training(dev, per_batch, global_batch, K, W, barrier, dist_mod=None, host_inputs=False):
+    """K optimizer iterations (model/model.py:48-58: forward in train() mode incl. Dropout -> backward -> Adam, gradient all-reduce overlapped
+    with the backward when world > 1) of sr_sr3_16_128.json on this rank's slice of the global batch.  CUDA events, max over ranks.
+    host_inputs: HR / SR come from pinned host memory every step and the loss value is read back (the end-to-end form)."""
+    import torch
+    import sr3_b200
+    from sr3_b200 import parallel
+    torch.manual_seed(0)
+    opt = make_opt(SCHED)
+    opt["phase"] = "train"                              # orthogonal init (networks.py:110-112)
+    net = sr3_b200.define_G(opt).to(dev)
+    net.set_loss(dev)
+    net.set_new_noise_schedule(SCHED, dev)
+    net.train()
+    g = torch.Generator().manual_seed(5)
+    hr_h = (torch.rand(per_batch, 3, IMAGE, IMAGE, generator=g) * 2 - 1).pin_memory()
+    sr_h = (torch.rand(per_batch, 3, IMAGE, IMAGE, generator=g) * 2 - 1).pin_memory()
+    hr_d, sr_d = hr_h.to(dev), sr_h.to(dev)
+    tr = parallel.DataParallelTrainer(net, lr=1e-4)
+    losses = []
+
+    def one():
+        if host_inputs:
+            losses.append(tr.step(hr_h.to(dev, non_blocking=True), sr_h.to(dev, non_blocking=True), global_batch=global_batch))
+        else:
+            losses.append(tr.step(hr_d, sr_d, global_batch=global_batch))
+
+    for _ in range(W):
+        one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        one()
+    e1.record()
+    barrier()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist_mod is not None:
+        dist_mod.all_reduce(t_ms, op=dist_mod.ReduceOp.MAX)
+    comm_ms = tr.comm_window_ms()
+    eng = tr._eng
+    n_blocks = eng.num_backward_blocks()
+    n_buckets = len(tr.buckets.slices)
+    import math
+    assert all(math.isfinite(l) for l in losses), "training loss is not finite"
+    del tr, net
+    torch.cuda.empty_cache()
+    return float(t_ms.item()) / K, comm_ms, losses, n_blocks, n_buckets
+
+
+def run_train(args, rank, local, world):
+    """--workload train: BASELINE.json configs[3] -- sr_sr3_16_128.json training step (fwd + bwd + Adam), global batch 64, data parallel."""
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    import torch
+    import torch.distributed as dist
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    GB = args.train_batch
+    assert GB % world == 0
+    per = GB // world
+    W, K = max(args.warmup, 3), args.steps
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dd = dist if world > 1 else None
+    with ClockSampler(local) as clk:
+        ms, comm_ms, losses, n_blocks, n_buckets = time_training(dev, per, GB, K, W, barrier, dd, host_inputs=False)
+    e2e_ms, _, _, _, _ = time_training(dev, per, GB, max(3, K // 2), 3, barrier, dd, host_inputs=True)
+    if rank == 0:
+        peaks = measured_peaks()
+        fl = 3.0 * algorithmic_flops_per_image() * GB          # fwd + dgrad + wgrad (SURVEY.md 8d: 277 GFLOP per image)
+        img_bytes = per * 3 * IMAGE * IMAGE * 4
+        line = {"metric": "training steps/sec (sr_sr3_16_128 fwd+bwd+Adam, global batch %d)" % GB, "value": 1e3 / ms, "unit": "steps/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "sr_sr3_16_128.json training step (configs[3]): p_losses in train() mode (Dropout 0.2) + backward + Adam, random-init "
+                                       "(orthogonal) weights, synthetic HR/SR in [-1,1]", "global_batch": GB, "per_gpu_batch": per,
+                           "parallelism": f"data parallel x{world}: %d gradient buckets all-reduced (NCCL sum) while the backward of the earlier layers runs; Adam on every rank" % n_buckets,
+                           "l2": "per-step working set (activations kept for the backward, several GB) exceeds the 126 MB L2; no explicit flush",
+                           "images_per_s": GB * 1e3 / ms},
+                "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": 2 * img_bytes, "d2h_bytes_per_step": 8,
+                        "api": "sr3_b200.parallel.DataParallelTrainer.step on pinned host HR / SR tensors, loss value read back every step"},
+                "gpu_launches": None, "allreduce_window_ms": comm_ms, "backward_blocks": n_blocks,
+                "clocks": clk.summary(),
+                "roofline": {"bound": "tensor", "kernel": "whole training step (forward tile kernel + data-gradient tile kernel + wgrad_kernel)", "achieved": fl / world / (ms * 1e-3) / 1e12,
+                             "peak": peaks["burst"], "unit": "TFLOP/s", "frac": fl / world / (ms * 1e-3) / 1e12 / peaks["burst"], "traffic": None,
+                             "algorithmic_flops_per_step_per_gpu": fl / world, "peak_source": peaks["src"]},
+                "cpu_baseline": None, "losses_first_last": [losses[0], losses[-1]]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
@@ -309,12 +422,17 @@ def main():
                     help="N>1: strong (default, the metric as defined) = ONE batch of 16 images sharded over the GPUs; "
                          "weak = every GPU samples its own batch of 16 images (global batch 16N, value in batch-16 steps/s)")
     ap.add_argument("--profile-out", default=None, help="write the per-op timing table of one step to this JSON file")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample (default): the BASELINE metric; train: configs[3], the training step (fwd + bwd + Adam) at global batch --train-batch")
+    ap.add_argument("--train-batch", type=int, default=64)
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.workload == "train":
+        return run_train(args, rank, local, world)
 
     if world > 1:
         # communicator set-up at INFO on STDERR (stdout carries exactly one JSON line): the rank count of the job is checkable from the log
