@@ -289,7 +289,7 @@ class Engine:
         ms = (c_float * 8)()
         with torch.cuda.device(self.device):
             _check(lib().sr3_train_backward_profile(self._h, float(grad_scale), arr, len(grads), ms, _stream()))
-        names = {0: "dgrad_tile_kernel", 1: "groupnorm_elementwise", 4: "other", 6: "wgrad", 7: "attention_gemms"}
+        names = {0: "dgrad_tile_kernel", 1: "groupnorm_elementwise", 4: "other", 5: "wgrad_slice_reduce", 6: "wgrad", 7: "attention_gemms"}
         return {names.get(k, str(k)): ms[k] for k in range(8) if ms[k] > 0}
 
     def num_backward_blocks(self):

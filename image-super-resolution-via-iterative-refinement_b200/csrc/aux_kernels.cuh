@@ -334,20 +334,24 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ wf,
 }
 
 // OIHW fp32 conv weight -> K-major bf16 GEMM operand: dst[o][k_off + (r*KW+s)*cin_pad + c]
-// precise mode (lo_off != 0): the row is [hi (ktot) | lo (ktot)], lo_off = ktot; `ld` = row length in elements
+// precise mode (lo_off != 0): the row is [hi (ktot) | lo (ktot)], lo_off = ktot; `ld` = row length in elements.
+// One thread per (o, c): it reads the KH*KW contiguous taps of that pair (the warp reads one contiguous span) and writes tap by tap (for a
+// fixed tap the warp's c are contiguous in dst): both sides coalesced.  Runs after every optimizer step of the training loop.
 __global__ void __launch_bounds__(256) pack_conv_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin,
                                                                int KH, int KW, int ld, int k_off, int cin_pad, int lo_off) {
-    const long long total = static_cast<long long>(Cout) * Cin * KH * KW;
+    const long long total = static_cast<long long>(Cout) * Cin;
+    const int taps = KH * KW;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        long long r = i;
-        const int s = static_cast<int>(r % KW); r /= KW;
-        const int rr = static_cast<int>(r % KH); r /= KH;
-        const int c = static_cast<int>(r % Cin);
-        const int o = static_cast<int>(r / Cin);
-        const long long di = static_cast<long long>(o) * ld + k_off + (rr * KW + s) * cin_pad + c;
-        dst[di] = __float2bfloat16_rn(src[i]);
-        if (lo_off) dst[di + lo_off] = __float2bfloat16_rn(bf16_residual(src[i]));
+        const int c = static_cast<int>(i % Cin);
+        const int o = static_cast<int>(i / Cin);
+        const float* sp = src + i * taps;
+        for (int t = 0; t < taps; ++t) {
+            const float v = sp[t];
+            const long long di = static_cast<long long>(o) * ld + k_off + t * cin_pad + c;
+            dst[di] = __float2bfloat16_rn(v);
+            if (lo_off) dst[di + lo_off] = __float2bfloat16_rn(bf16_residual(v));
+        }
     }
 }
 

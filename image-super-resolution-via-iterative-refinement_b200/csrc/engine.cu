@@ -807,7 +807,7 @@ struct sr3_engine {
         if (dry) return;
         const int ld = PW * ktot, lo_off = precise ? ktot : 0;
         add_param(name, {Cout, Cin, k, k}, [=](const float* src, cudaStream_t st) {
-            const long long total = 1LL * Cout * Cin * k * k;
+            const long long total = 1LL * Cout * Cin;
             const int blocks = (int)std::min<long long>((total + 255) / 256, 4096);
             pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(src, dst, Cout, Cin, k, k, ld, k_off, cin_pad, lo_off);
             CK(cudaGetLastError());

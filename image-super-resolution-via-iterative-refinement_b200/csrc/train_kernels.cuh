@@ -11,17 +11,18 @@
 namespace sr3 {
 
 // ------------------------------------------------------------------------------------------------ weight packers for the data gradients
-// dgrad of conv (stride 1, k in {1,3}): dX = conv(dY, W') with W'[ci][((k-1-r)*k + (k-1-s)) * cout_pad + co] = W[co][ci][r][s]
+// dgrad of conv (stride 1, k in {1,3}): dX = conv(dY, W') with W'[ci][((k-1-r)*k + (k-1-s)) * cout_pad + co] = W[co][ci][r][s].
+// One thread per (c, o), o fastest: the k*k taps of a pair are contiguous in src, and for a fixed tap the warp's o are contiguous in dst.
 __global__ void __launch_bounds__(256) pack_dgrad_weight_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int Cout, int Cin, int k,
                                                                 int cout_pad, int ld) {
-    const long long total = static_cast<long long>(Cout) * Cin * k * k;
+    const long long total = static_cast<long long>(Cout) * Cin;
+    const int taps = k * k;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        long long r = i;
-        const int s = static_cast<int>(r % k); r /= k;
-        const int rr = static_cast<int>(r % k); r /= k;
-        const int c = static_cast<int>(r % Cin);
-        const int o = static_cast<int>(r / Cin);
-        dst[static_cast<long long>(c) * ld + ((k - 1 - rr) * k + (k - 1 - s)) * cout_pad + o] = __float2bfloat16_rn(src[i]);
+        const int o = static_cast<int>(i % Cout);
+        const int c = static_cast<int>(i / Cout);
+        const float* sp = src + (static_cast<long long>(o) * Cin + c) * taps;
+        __nv_bfloat16* dp = dst + static_cast<long long>(c) * ld + o;
+        for (int t = 0; t < taps; ++t) dp[(taps - 1 - t) * cout_pad] = __float2bfloat16_rn(sp[t]);     // (k-1-r)*k + (k-1-s) = k*k-1 - (r*k+s)
     }
 }
 // dgrad of the stride-2 Downsample conv (unet.py:68-74) as four output-parity phases on the low-resolution dY grid (the same op shape as the
@@ -89,7 +90,7 @@ struct WgradParams {
     CUtensorMap dy_map;      // 5-D bf16 (Cout, OW, 1, OH, B), box {64, 8, 1, 8, 1}
     CUtensorMap x_map;       // 5-D bf16 view of X, box {64, 8, 1, 8, 1}
     float* ws;               // [slices][co_pad][ntaps][Cin]
-    int Cin, co_pad, OH, OW, B;
+    int Cin, co_pad, cout_valid, OH, OW, B;
     int ntaps, taps_per_cta;
     int patches;             // B * (OH/8) * (OW/8)
     int slices;
@@ -172,7 +173,9 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
             if (++s == WGRAD_STAGES) { s = 0; ph ^= 1u; }
         }
     } else if (warp == 1) {
-        constexpr uint32_t IDESC = umma_idesc_bf16_mn(128, 64);
+        // the X boxes of the CTA's taps lie 8192 B apart = the panel stride (LBO) of an MN-major operand: ONE UMMA of N = 64 * taps covers all
+        // of them (accumulator columns [tap * 64 + ci]), so the dY tile is read from shared memory once per K step, not once per tap
+        const uint32_t idesc = umma_idesc_bf16_mn(128, 64 * nt);
         int s = 0;
         uint32_t ph = 0;
         for (int it = 0; it < iters; ++it) {
@@ -183,10 +186,8 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk) {                       // 16 pixels = two 8-pixel atoms per UMMA
                     const uint64_t adesc = umma_desc_mnmajor_sw128(st + kk * 2048, 8192, 1024);
-                    for (int t = 0; t < nt; ++t) {
-                        const uint64_t bdesc = umma_desc_mnmajor_sw128(st + 16384 + t * 8192 + kk * 2048, 8192, 1024);
-                        umma_bf16_ss(tmem_base + t * 64, adesc, bdesc, IDESC, (it | kk) != 0);
-                    }
+                    const uint64_t bdesc = umma_desc_mnmajor_sw128(st + 16384 + kk * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem_base, adesc, bdesc, idesc, (it | kk) != 0);
                 }
                 umma_commit(empty_bar(s));
                 if (it == iters - 1) umma_commit(acc_full);
@@ -214,6 +215,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
+                if (co >= p.cout_valid) continue;               // padded rows of the 128-row tile (Cout = 64 / 3): nobody reads them
                 float4* dst = reinterpret_cast<float4*>(p.ws + ((static_cast<long long>(slice) * p.co_pad + co) * p.ntaps + tap0 + t) * p.Cin + ci0 + ch * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
@@ -226,21 +228,43 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
     if (warp == 1) tmem_dealloc(tmem_base, 256);
 }
 
-// grad[co][ci][tap] (OIHW) = gscale * sum over slices of ws[slice][co][tap][ci]   (ci < cin_valid, co < cout_valid)
+// grad[co][ci][tap] (OIHW) = gscale * sum over slices of ws[slice][co][tap][ci]   (ci < cin_valid, co < cout_valid).
+// One block per (co, 32 input channels): warp w sums slices w, w + 8, ... for every tap of input channel ci0 + lane (coalesced 128 B rows, nine
+// independent loads in flight), the eight partial sums meet in shared memory laid out [ci][tap] = the OIHW order and are added in warp order
+// (deterministic), then written as one contiguous span.
+constexpr int WRED_CI = 32;
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int slices, int co_pad, int ntaps, int Cin,
                                                            int cout_valid, int cin_valid, float gscale) {
     pdl_launch_dependents();
     pdl_wait();
-    const long long total = static_cast<long long>(cout_valid) * ntaps * cin_valid;
+    __shared__ float sm[8][WRED_CI * WGRAD_MAX_TAPS];
+    const int co = blockIdx.y;
+    const int ci0 = blockIdx.x * WRED_CI;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ci = ci0 + lane;
     const long long sstride = static_cast<long long>(co_pad) * ntaps * Cin;
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int ci = static_cast<int>(i % cin_valid);
-        const int tap = static_cast<int>((i / cin_valid) % ntaps);
-        const int co = static_cast<int>(i / (static_cast<long long>(cin_valid) * ntaps));
-        const float* s = ws + (static_cast<long long>(co) * ntaps + tap) * Cin + ci;
-        float acc = 0.f;
-        for (int k = 0; k < slices; ++k) acc += s[k * sstride];
-        grad[(static_cast<long long>(co) * cin_valid + ci) * ntaps + tap] = acc * gscale;
+    float acc[WGRAD_MAX_TAPS];
+#pragma unroll
+    for (int t = 0; t < WGRAD_MAX_TAPS; ++t) acc[t] = 0.f;
+    if (ci < cin_valid) {
+        const float* s = ws + static_cast<long long>(co) * ntaps * Cin + ci;
+        for (int k = w; k < slices; k += 8) {
+#pragma unroll
+            for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
+                if (t < ntaps) acc[t] += __ldcg(&s[k * sstride + static_cast<long long>(t) * Cin]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
+        if (t < ntaps) sm[w][lane * ntaps + t] = acc[t];
+    __syncthreads();
+    const int nci = min(WRED_CI, cin_valid - ci0);
+    float* g = grad + (static_cast<long long>(co) * cin_valid + ci0) * ntaps;
+    for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a += sm[k][i];
+        g[i] = a * gscale;
     }
 }
 
@@ -258,6 +282,7 @@ struct GnBwdParams {
     int add_ld;
     float* dst0; int acc0; __nv_bfloat16* dst0_b; float* gsum0; int gsum_ld0;    // gradient of source 0: [B][HW][C0]; acc: dst += ; gsum[b * ld + c] += column sums
     float* dst1; int acc1; __nv_bfloat16* dst1_b; float* gsum1; int gsum_ld1;    // source 1 (skip connection)
+    float* dgamma; float* dbeta; float gscale;   // pass 2, block (0, 0): dgamma[c] = gscale sum_b S2[b][c], dbeta[c] = gscale sum_b S1[b][c]
 };
 
 // mean / rstd per group into gm / gr (shared), from the fp64 channel sums.  scratch: [C] doubles.  Ends with __syncthreads().
@@ -309,6 +334,14 @@ __global__ void __launch_bounds__(512) gn_bwd_kernel(const GnBwdParams p) {
     const int b = blockIdx.y;
     groupnorm_mean_rstd(f, b, scratch, gm, gr);
     if (APPLY) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && (p.dgamma != nullptr || p.dbeta != nullptr)) {
+            for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                float a = 0.f, q = 0.f;
+                for (int bb = 0; bb < f.B; ++bb) { a += __ldcg(&p.sums[(static_cast<long long>(bb) * C + c) * 2]); q += __ldcg(&p.sums[(static_cast<long long>(bb) * C + c) * 2 + 1]); }
+                if (p.dgamma) p.dgamma[c] = q * p.gscale;
+                if (p.dbeta) p.dbeta[c] = a * p.gscale;
+            }
+        }
         // group means of gamma * S1, gamma * S2
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             const float g = __ldg(&f.gamma[c]);
@@ -350,43 +383,54 @@ __global__ void __launch_bounds__(512) gn_bwd_kernel(const GnBwdParams p) {
     const int acc = from0 ? p.acc0 : p.acc1;
     const int cl = from0 ? c : c - f.C0;
     if (threadIdx.x < vpp * kpix) {
-        for (int pix = pix0 + lp; pix < pix1; pix += kpix) {
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(src + (img + pix) * cs));
-            const float4 dv = __ldcg(reinterpret_cast<const float4*>(p.dA + (img + pix) * C + c));
-            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-            float d4[4] = {dv.x, dv.y, dv.z, dv.w};
-            if (p.drop && p.drop->p > 0.f) {
-                float sc[4];
-                drop_scale4(*p.drop, b, c, pix, C, f.HW, sc);
+        constexpr int U = 1;                          // (U = 4 measured slower: 124 registers per thread halve the resident blocks)
+        for (int pix = pix0 + lp; pix < pix1; pix += kpix * U) {
+            float4 xv[U], dv[U], av[U];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) d4[j] *= sc[j];
+            for (int u = 0; u < U; ++u) {
+                const int pp = pix + u * kpix;
+                if (pp < pix1) {
+                    xv[u] = __ldg(reinterpret_cast<const float4*>(src + (img + pp) * cs));
+                    dv[u] = __ldcg(reinterpret_cast<const float4*>(p.dA + (img + pp) * C + c));
+                    if (APPLY && p.add) av[u] = __ldcg(reinterpret_cast<const float4*>(p.add + (img + pp) * p.add_ld + c));
+                }
             }
-            float out[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float xh = (x4[j] - mu[j]) * rs[j];
-                float d = d4[j];
-                if (f.silu) {
-                    const float y = ga[j] * xh + be[j];
-                    const float sg = 1.0f / (1.0f + __expf(-y));
-                    d *= sg * (1.0f + y * (1.0f - sg));
-                }
-                if (APPLY) out[j] = rs[j] * (ga[j] * d - mm1[j] - xh * mm2[j]);
-                else { s1[j] += d; s2[j] += d * xh; }
-            }
-            if (APPLY) {
-                if (p.add) {
-                    const float4 av = __ldcg(reinterpret_cast<const float4*>(p.add + (img + pix) * p.add_ld + c));
-                    out[0] += av.x; out[1] += av.y; out[2] += av.z; out[3] += av.w;
-                }
-                if (dst) {
-                    float4* dp = reinterpret_cast<float4*>(dst + (img + pix) * cs + cl);
-                    if (acc) { const float4 o = *dp; out[0] += o.x; out[1] += o.y; out[2] += o.z; out[3] += o.w; }
-                    *dp = make_float4(out[0], out[1], out[2], out[3]);
-                }
-                if (dst_b) *reinterpret_cast<uint2*>(dst_b + (img + pix) * cs + cl) = pack_bf16x4(out[0], out[1], out[2], out[3]);
+            for (int u = 0; u < U; ++u) {
+                const int pp = pix + u * kpix;
+                if (pp >= pix1) continue;
+                const float x4[4] = {xv[u].x, xv[u].y, xv[u].z, xv[u].w};
+                float d4[4] = {dv[u].x, dv[u].y, dv[u].z, dv[u].w};
+                if (p.drop && p.drop->p > 0.f) {
+                    float sc[4];
+                    drop_scale4(*p.drop, b, c, pp, C, f.HW, sc);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cs4[j] += out[j];
+                    for (int j = 0; j < 4; ++j) d4[j] *= sc[j];
+                }
+                float out[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float xh = (x4[j] - mu[j]) * rs[j];
+                    float d = d4[j];
+                    if (f.silu) {
+                        const float y = ga[j] * xh + be[j];
+                        const float sg = 1.0f / (1.0f + __expf(-y));
+                        d *= sg * (1.0f + y * (1.0f - sg));
+                    }
+                    if (APPLY) out[j] = rs[j] * (ga[j] * d - mm1[j] - xh * mm2[j]);
+                    else { s1[j] += d; s2[j] += d * xh; }
+                }
+                if (APPLY) {
+                    if (p.add) { out[0] += av[u].x; out[1] += av[u].y; out[2] += av[u].z; out[3] += av[u].w; }
+                    if (dst) {
+                        float4* dp = reinterpret_cast<float4*>(dst + (img + pp) * cs + cl);
+                        if (acc) { const float4 o = *dp; out[0] += o.x; out[1] += o.y; out[2] += o.z; out[3] += o.w; }
+                        *dp = make_float4(out[0], out[1], out[2], out[3]);
+                    }
+                    if (dst_b) *reinterpret_cast<uint2*>(dst_b + (img + pp) * cs + cl) = pack_bf16x4(out[0], out[1], out[2], out[3]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) cs4[j] += out[j];
+                }
             }
         }
     }
