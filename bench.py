@@ -556,19 +556,20 @@ def main():
         for d in by_op.values():
             d["GB_per_s"] = round(d.pop("bytes") / (d["us"] * 1e-6) / 1e9, 1) if d["us"] > 0 else None
     achieved = alg_flops_step / (kernel_ms * 1e-3) / 1e12
-    traffic, traffic_src = None, None
+    traffic, traffic_src, whole_step_traffic = None, None, None
     for cand in ("r02_traffic.json", "r01_traffic.json"):
         tpath = os.path.join(ROOT, "profiles", cand)
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
             key = "step_kernel_dram_bytes_per_launch" if step_prof is not None else "gemm_tile_kernel_dram_bytes_per_step"
             if key in tj:
-                traffic, traffic_src = tj[key], "profiles/" + cand + " (ncu --set full of this build: dram__bytes_read.sum + dram__bytes_write.sum)"
+                traffic, traffic_src = tj[key], "profiles/" + cand + " (ncu per-launch dram__bytes_read.sum + dram__bytes_write.sum of one step of this build)"
+                whole_step_traffic = tj.get("whole_step_dram_bytes")
                 break
     roof = {"bound": "tensor", "kernel": kernel_name, "achieved": achieved, "peak": peaks["burst"], "unit": "TFLOP/s",
             "frac": achieved / peaks["burst"], "frac_of_sustained_peak": achieved / peaks["sustained"], "peak_sustained": peaks["sustained"],
             "peak_source": peaks["src"] + ": frac is against the BURST bf16 figure", "traffic": traffic, "traffic_source": traffic_src,
-            "algorithmic_flops_per_launch": alg_flops_step, "algorithmic_bytes_per_launch": 2.98e9 * per / 16.0,
+            "traffic_whole_step_incl_groupnorm_apply": whole_step_traffic, "algorithmic_flops_per_launch": alg_flops_step, "algorithmic_bytes_per_launch": 2.98e9 * per / 16.0,
             "kernel_ms_per_launch": kernel_ms, "launches_per_step": eng.launches_per_step(), "ops_per_step": eng.ops_per_step(),
             "frac_of_nominal_bound": (0.732 * per / 16.0) / (ms / K) if per == 16 else None,
             "step_frac_of_burst_peak": (alg_flops_step / (ms / K * 1e-3) / 1e12) / peaks["burst"], "by_op": by_op}
