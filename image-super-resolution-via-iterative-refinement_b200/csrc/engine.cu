@@ -691,6 +691,14 @@ struct sr3_engine {
     std::vector<Op>* bwd_sink = nullptr;                   // where push() records while a layer's backward is being described
     std::vector<std::vector<Op>> bwd_blocks;               // one op list per forward layer, executed last to first
     std::vector<std::vector<int>> bwd_kinds;               // op kinds (profiling): 0 data-gradient tile kernel, 1 GroupNorm / elementwise, 4 other, 6 weight gradient, 7 attention GEMMs
+    // single-launch re-pack (bf16 precision): one PackDesc per packed copy, its source = parameter `pack_src[i]` (second source of a fused
+    // bias: `pack_src2[i]`); device table rebuilt only when the parameter pointers change
+    std::vector<PackDesc> pack_descs; std::vector<int> pack_src, pack_src2;
+    PackDesc* pack_dev = nullptr; std::vector<const float*> pack_last_ptrs;
+    void add_pack(const std::string& pname, PackDesc d, const std::string& pname2 = "") {
+        if (dry || precise) return;
+        pack_descs.push_back(d); pack_src.push_back(pindex.at(pname)); pack_src2.push_back(pname2.empty() ? -1 : pindex.at(pname2));
+    }
     std::vector<float*> grad_dst;                          // per parameter (state_dict order): where the running backward writes its gradient
     float gscale = 1.f;                                    // d(total) / d(summed loss) of the running backward (1 / (b c h w), model.py:50-53)
     float* zero_arena = nullptr; size_t zero_cap = 0, zero_used = 0;    // everything the backward accumulates into (cleared at its start)
@@ -794,6 +802,7 @@ struct sr3_engine {
         int64_t n = 1; for (auto s : shape) n *= s;
         float* dst = static_cast<float*>(mem.alloc(n * sizeof(float)));
         add_param(name, shape, [dst, n](const float* src, cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
+        { PackDesc d{}; d.type = 0; d.dst = dst; d.n = n; add_pack(name, d); }
         return dst;
     }
     // f32 parameter stored into a slice of a bigger array
@@ -801,6 +810,7 @@ struct sr3_engine {
         if (dry) return;
         int64_t n = 1; for (auto s : shape) n *= s;
         add_param(name, shape, [dst, n](const float* src, cudaStream_t st) { CK(cudaMemcpyAsync(dst, src, n * sizeof(float), cudaMemcpyDeviceToDevice, st)); });
+        { PackDesc d{}; d.type = 0; d.dst = dst; d.n = n; add_pack(name, d); }
     }
     // conv weight packed into rows [0,Cout) of a [rows_pad][ktot] bf16 matrix at column k_off
     void conv_weight_param(const std::string& name, bf16* dst, int Cout, int Cin, int k, int ktot, int k_off, int cin_pad) {
@@ -812,6 +822,7 @@ struct sr3_engine {
             pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(src, dst, Cout, Cin, k, k, ld, k_off, cin_pad, lo_off);
             CK(cudaGetLastError());
         });
+        { PackDesc d{}; d.type = 1; d.dst = dst; d.Cout = Cout; d.Cin = Cin; d.k = k; d.ld = ld; d.k_off = k_off; d.cin_pad = cin_pad; add_pack(name, d); }
     }
     bf16* new_weight(int rows, int ktot, int block_n) {      // [rows_pad][PW * ktot]: precise mode appends the low halves of every row
         if (dry) return nullptr;
@@ -952,6 +963,7 @@ struct sr3_engine {
                 bias_total = static_cast<float*>(mem.alloc(cout * sizeof(float)));
                 float* bt = bias_total;
                 finalize_ops.push_back([=](cudaStream_t st) { add_vec_kernel<<<(cout + 255) / 256, 256, 0, st>>>(cb2, cbr, bt, cout); CK(cudaGetLastError()); });
+                { PackDesc d{}; d.type = 6; d.dst = bt; d.n = cout; add_pack(p + ".block2.block.3.bias", d, p + ".res_conv.bias"); }
             }
         }
         // scratch
@@ -1261,6 +1273,7 @@ struct sr3_engine {
                         fold_upsample_weight_kernel<<<(int)std::min<long long>((total + 255) / 256, 4096), 256, 0, st>>>(src, w0, w1, w2, w3, C, C, ldw, low);
                         CK(cudaGetLastError());
                     });
+                    { PackDesc d{}; d.type = 5; d.dst = w0; d.Cout = C; d.Cin = C; d.ld = ldw; d.n = (long long)rows_pad * 4 * C * PW; add_pack(L.name + ".conv.weight", d); }
                 }
                 float* b = f32_param(L.name + ".conv.bias", {C});
                 bf16* raw = (train && fuse_cast) ? last_xraw : static_cast<bf16*>(role(fuse_cast ? "xraw" : "raw", (size_t)Bp * Hl * Wl * C * 2 * PW));
@@ -1651,8 +1664,24 @@ int sr3_engine_load_all_params(sr3_engine* e, const float* const* srcs, int n, v
     REQUIRE(e && srcs && n == (int)e->params.size(), "expected %d parameter pointers", e ? (int)e->params.size() : 0);
     CK(cudaSetDevice(e->dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    for (int i = 0; i < n; ++i) REQUIRE(srcs[i] != nullptr, "null pointer for %s", e->params[i].name.c_str());
+    if (!e->pack_descs.empty() && !e->precise && getenv("SR3_NO_PACK_TABLE") == nullptr) {
+        // one launch over the descriptor table (rebuilt only when a parameter moved)
+        const size_t nd = e->pack_descs.size();
+        if (e->pack_last_ptrs.size() != (size_t)n || memcmp(e->pack_last_ptrs.data(), srcs, n * sizeof(float*)) != 0 || !e->pack_dev) {
+            std::vector<PackDesc> tab = e->pack_descs;
+            for (size_t i = 0; i < nd; ++i) { tab[i].src = srcs[e->pack_src[i]]; tab[i].src2 = e->pack_src2[i] >= 0 ? srcs[e->pack_src2[i]] : nullptr; }
+            if (!e->pack_dev) e->pack_dev = static_cast<PackDesc*>(e->mem.alloc(nd * sizeof(PackDesc)));
+            CK(cudaMemcpyAsync(e->pack_dev, tab.data(), nd * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
+            CK(cudaStreamSynchronize(st));                 // `tab` is pageable host memory
+            e->pack_last_ptrs.assign(srcs, srcs + n);
+        }
+        pack_all_kernel<<<dim3(32, (unsigned)std::min<size_t>(nd, 65535)), 256, 0, st>>>(e->pack_dev, (int)nd);
+        CK(cudaGetLastError());
+        for (auto& p : e->params) p.loaded = true;
+        return 0;
+    }
     for (int i = 0; i < n; ++i) {
-        REQUIRE(srcs[i] != nullptr, "null pointer for %s", e->params[i].name.c_str());
         ParamEntry& p = e->params[i];
         p.load(srcs[i], st);
         for (auto& h : p.hooks) h(srcs[i], st);

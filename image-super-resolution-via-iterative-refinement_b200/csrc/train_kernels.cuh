@@ -740,4 +740,109 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamTensor* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------------ one launch for the whole re-pack
+// After every optimizer step all packed copies of the fp32 parameters are refreshed (forward K-major weights, data-gradient weights, folded
+// Upsample phases, Downsample / Upsample data-gradient kernels, plain fp32 copies of the GroupNorm / bias / Linear parameters, fused bias
+// vectors).  As separate launches that is ~470 tiny stream operations per step; this kernel walks a device table instead: blockIdx.y = entry,
+// blockIdx.x / gridDim.x stride over the entry's elements.
+struct PackDesc {
+    int type;                 // 0 fp32 copy, 1 forward conv weight, 2 stride-1 data-gradient weight, 3 Downsample data-gradient phases,
+                              // 4 Upsample data-gradient 4x4 kernel, 5 folded Upsample forward phases, 6 dst = src + src2 (fused bias)
+    int Cout, Cin, k, ld, k_off, cin_pad, rows_pad;
+    const float* src; const float* src2;
+    void* dst;
+    long long n;              // type 0 / 6: elements;  type 5: element stride between the four phase matrices
+};
+__device__ __forceinline__ void pack_entry(const PackDesc& d, long long i0, long long stride) {
+    __nv_bfloat16* db = static_cast<__nv_bfloat16*>(d.dst);
+    switch (d.type) {
+    case 0: { float* o = static_cast<float*>(d.dst); for (long long i = i0; i < d.n; i += stride) o[i] = d.src[i]; break; }
+    case 6: { float* o = static_cast<float*>(d.dst); for (long long i = i0; i < d.n; i += stride) o[i] = d.src[i] + d.src2[i]; break; }
+    case 1: {
+        const int taps = d.k * d.k;
+        const long long total = static_cast<long long>(d.Cout) * d.Cin;
+        for (long long i = i0; i < total; i += stride) {
+            const int c = static_cast<int>(i % d.Cin), o = static_cast<int>(i / d.Cin);
+            const float* sp = d.src + i * taps;
+            for (int t = 0; t < taps; ++t) db[static_cast<long long>(o) * d.ld + d.k_off + t * d.cin_pad + c] = __float2bfloat16_rn(sp[t]);
+        }
+        break;
+    }
+    case 2: {
+        const int taps = d.k * d.k;
+        const long long total = static_cast<long long>(d.Cout) * d.Cin;
+        for (long long i = i0; i < total; i += stride) {
+            const int o = static_cast<int>(i % d.Cout), c = static_cast<int>(i / d.Cout);
+            const float* sp = d.src + (static_cast<long long>(o) * d.Cin + c) * taps;
+            __nv_bfloat16* dp = db + static_cast<long long>(c) * d.ld + o;
+            for (int t = 0; t < taps; ++t) dp[(taps - 1 - t) * d.cin_pad] = __float2bfloat16_rn(sp[t]);      // cin_pad holds cout_pad here
+        }
+        break;
+    }
+    case 3: {
+        const long long total = 4LL * d.Cin * 4 * d.Cout;
+        for (long long i = i0; i < total; i += stride) {
+            long long r = i;
+            const int o = static_cast<int>(r % d.Cout); r /= d.Cout;
+            const int ab = static_cast<int>(r % 4); r /= 4;
+            const int c = static_cast<int>(r % d.Cin);
+            const int ph = static_cast<int>(r / d.Cin);
+            const int py = ph >> 1, px = ph & 1, a = ab >> 1, b = ab & 1;
+            const int rr = py == 0 ? (a == 1 ? 1 : -1) : (a == 0 ? 2 : 0);
+            const int ss = px == 0 ? (b == 1 ? 1 : -1) : (b == 0 ? 2 : 0);
+            const float v = (rr < 0 || ss < 0) ? 0.f : d.src[((static_cast<long long>(o) * d.Cin + c) * 3 + rr) * 3 + ss];
+            db[(static_cast<long long>(ph) * d.rows_pad + c) * (4LL * d.Cout) + ab * d.Cout + o] = __float2bfloat16_rn(v);
+        }
+        break;
+    }
+    case 4: {
+        const long long total = static_cast<long long>(d.Cin) * 16 * d.Cout;
+        for (long long i = i0; i < total; i += stride) {
+            long long r = i;
+            const int o = static_cast<int>(r % d.Cout); r /= d.Cout;
+            const int uv = static_cast<int>(r % 16);
+            const int c = static_cast<int>(r / 16);
+            const int u = uv >> 2, v = uv & 3;
+            float acc = 0.f;
+            for (int e = 0; e < 2; ++e) {
+                const int rr = e + 2 - u;
+                if (rr < 0 || rr > 2) continue;
+                for (int f = 0; f < 2; ++f) {
+                    const int ss = f + 2 - v;
+                    if (ss < 0 || ss > 2) continue;
+                    acc += d.src[((static_cast<long long>(o) * d.Cin + c) * 3 + rr) * 3 + ss];
+                }
+            }
+            db[static_cast<long long>(c) * (16LL * d.Cout) + uv * d.Cout + o] = __float2bfloat16_rn(acc);
+        }
+        break;
+    }
+    case 5: {
+        const long long total = 4LL * d.Cout * d.Cin * 4;
+        for (long long i = i0; i < total; i += stride) {
+            long long r = i;
+            const int c = static_cast<int>(r % d.Cin); r /= d.Cin;
+            const int ab = static_cast<int>(r % 4); r /= 4;
+            const int o = static_cast<int>(r % d.Cout);
+            const int ph = static_cast<int>(r / d.Cout);
+            const int py = ph >> 1, px = ph & 1, a = ab >> 1, b = ab & 1;
+            const int r0 = (py == 0) ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = (py == 0) ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+            const int s0 = (px == 0) ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = (px == 0) ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+            float acc = 0.f;
+            for (int rr = r0; rr <= r1; ++rr)
+                for (int ss = s0; ss <= s1; ++ss) acc += d.src[((static_cast<long long>(o) * d.Cin + c) * 3 + rr) * 3 + ss];
+            db[ph * d.n + static_cast<long long>(o) * d.ld + ab * d.Cin + c] = __float2bfloat16_rn(acc);
+        }
+        break;
+    }
+    default: break;
+    }
+}
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackDesc* __restrict__ tab, int n_entries) {
+    for (int e = blockIdx.y; e < n_entries; e += gridDim.y) {
+        const PackDesc d = tab[e];
+        pack_entry(d, blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
+    }
+}
+
 }  // namespace sr3
