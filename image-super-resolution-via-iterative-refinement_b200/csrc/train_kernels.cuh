@@ -229,26 +229,29 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 }
 
 // grad[co][ci][tap] (OIHW) = gscale * sum over slices of ws[slice][co][tap][ci]   (ci < cin_valid, co < cout_valid).
-// One block per (co, 32 input channels): warp w sums slices w, w + 8, ... for every tap of input channel ci0 + lane (coalesced 128 B rows, nine
-// independent loads in flight), the eight partial sums meet in shared memory laid out [ci][tap] = the OIHW order and are added in warp order
-// (deterministic), then written as one contiguous span.
-constexpr int WRED_CI = 32;
+// One block per (co, chunk of input channels): its eight warps are split into `sw` slice lanes x 8/sw groups of 32 input channels (sw = 8, 4,
+// 2 or 1 by the slice count, so no warp idles); a warp sums its slices for every tap of its 32 channels (coalesced 128 B rows, nine independent
+// loads in flight), the partial sums meet in shared memory laid out [ci][tap] = the OIHW order, are added in warp order (deterministic) and
+// written as one contiguous span.  (Finalising inside wgrad_kernel by the last-arriving CTA of a tile was measured slower: its 4-byte stores
+// at a 36-byte stride and the serial tail cost more than the launch they save.)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int slices, int co_pad, int ntaps, int Cin,
-                                                           int cout_valid, int cin_valid, float gscale) {
+                                                           int cout_valid, int cin_valid, float gscale, int sw) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float sm[8][WRED_CI * WGRAD_MAX_TAPS];
+    __shared__ float sm[8][32 * WGRAD_MAX_TAPS];
+    const int groups = 8 / sw;                       // 32-channel groups per block
     const int co = blockIdx.y;
-    const int ci0 = blockIdx.x * WRED_CI;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int ci = ci0 + lane;
+    const int grp = w / sw, sl = w % sw;
+    const int ci0 = blockIdx.x * 32 * groups;
+    const int ci = ci0 + grp * 32 + lane;
     const long long sstride = static_cast<long long>(co_pad) * ntaps * Cin;
     float acc[WGRAD_MAX_TAPS];
 #pragma unroll
     for (int t = 0; t < WGRAD_MAX_TAPS; ++t) acc[t] = 0.f;
     if (ci < cin_valid) {
         const float* s = ws + static_cast<long long>(co) * ntaps * Cin + ci;
-        for (int k = w; k < slices; k += 8) {
+        for (int k = sl; k < slices; k += sw) {
 #pragma unroll
             for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
                 if (t < ntaps) acc[t] += __ldcg(&s[k * sstride + static_cast<long long>(t) * Cin]);
@@ -258,12 +261,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
         if (t < ntaps) sm[w][lane * ntaps + t] = acc[t];
     __syncthreads();
-    const int nci = min(WRED_CI, cin_valid - ci0);
+    const int nci = min(32 * groups, cin_valid - ci0);
     float* g = grad + (static_cast<long long>(co) * cin_valid + ci0) * ntaps;
     for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
+        const int gi = i / (32 * ntaps), r = i - gi * 32 * ntaps;      // channel group, position inside its [32][ntaps] slab
         float a = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) a += sm[k][i];
+        for (int k = 0; k < sw; ++k) a += sm[gi * sw + k][r];
         g[i] = a * gscale;
     }
 }
