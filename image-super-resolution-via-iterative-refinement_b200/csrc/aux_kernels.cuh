@@ -65,6 +65,7 @@ struct PrepParams {
     int B, items_per_image;                 // persistent step kernel: work items = B x items_per_image blocks of pix_per_block pixels
     int precise;                            // 1: operands are (hi | lo) pairs -- out rows are 2 (C0+C1) wide, low halves C0+C1 elements behind
     const DropSpec* drop;                   // training-mode forward only: Dropout after the SiLU (unet.py:86); nullptr otherwise
+    float* save_mr;                         // training-mode forward only: [B][groups][2] (mean, rstd) kept for the backward; nullptr otherwise
 };
 
 // Per-(image, channel) scale / shift of a GroupNorm from the fp64 channel sums: y = x * sc[c] + sh[c].
@@ -134,6 +135,12 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
     float* gr = gm + p.groups;   // [groups] rstd
     const int b = blockIdx.y;
     groupnorm_scale_shift(p, b, sc, sh, gm, gr);
+    if (p.save_mr != nullptr && blockIdx.x == 0) {
+        for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
+            p.save_mr[(static_cast<long long>(b) * p.groups + g) * 2] = gm[g];
+            p.save_mr[(static_cast<long long>(b) * p.groups + g) * 2 + 1] = gr[g];
+        }
+    }
     const int vpp = C >> 2;                       // 4-channel vectors per pixel
     const int kpix = blockDim.x / vpp;            // pixels covered by the block per step
     const int c = (threadIdx.x % vpp) << 2;       // this thread's channels (constant)

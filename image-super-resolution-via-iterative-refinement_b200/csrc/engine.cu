@@ -857,10 +857,12 @@ struct sr3_engine {
     }
 
     // ---- layer builders -------------------------------------------------------------------------
+    float* last_mr = nullptr;              // training plan: (mean, rstd) buffer written by the most recent add_prep, read by its backward
     void add_prep(const Act& s0, const Act* s1, const float* gamma, const float* beta, int groups, bool silu, bf16* out_a, bf16* out_raw, const DropSpec* drop = nullptr) {
         if (dry) return;
         PrepParams p{};
         p.drop = drop;
+        if (train) { last_mr = static_cast<float*>(mem.alloc((size_t)Bp * groups * 2 * sizeof(float))); p.save_mr = last_mr; }
         p.src0 = s0.p; p.st0 = s0.stats; p.C0 = s0.C;
         p.src1 = s1 ? s1->p : nullptr; p.st1 = s1 ? s1->stats : nullptr; p.C1 = s1 ? s1->C : 0;
         p.gamma = gamma; p.beta = beta; p.groups = groups; p.HW = s0.H * s0.W; p.silu = silu ? 1 : 0; p.eps = 1e-5f;
@@ -975,6 +977,7 @@ struct sr3_engine {
         Act y = new_act(cout, Hh, Ww, L.attn ? "" : L.name);
 
         add_prep(x, skip, g1, b1, G, true, a1, raw);
+        float* mr1 = last_mr;
         {
             ConvArgs c; c.n_a = 1; c.a[0] = nhwc_src(a1, Bp, Hh, Ww, cin * PW); c.c0 = cin;
             add_conv_slabs(c.slabs, 0, cin, 3, 1, 0);
@@ -993,6 +996,7 @@ struct sr3_engine {
             }
         }
         add_prep(h, nullptr, g2, b2, G, true, a2, nullptr, drop);
+        float* mr2 = last_mr;
         {
             ConvArgs c; c.n_a = has_res ? 2 : 1; c.a[0] = nhwc_src(a2, Bp, Hh, Ww, cout * PW); c.c0 = cout;
             add_conv_slabs(c.slabs, 0, cout, 3, 1, 0);
@@ -1006,7 +1010,7 @@ struct sr3_engine {
         if (train) {
             if (!dry) film_slices.push_back({foff, cout, pid(p + ".noise_func.noise_func.0.weight"), pid(p + ".noise_func.noise_func.0.bias"), pid(p + ".block1.block.3.bias")});
             ResBwdCtx c; c.p = p; c.x = x; c.skip = skip; c.h = h; c.y = y; c.cin = cin; c.cout = cout; c.Hh = Hh; c.Ww = Ww; c.foff = foff;
-            c.has_res = has_res; c.x_acc = x_has_skip; c.a1 = a1; c.raw = raw; c.a2 = a2; c.g1 = g1; c.b1 = b1; c.g2 = g2; c.b2 = b2; c.drop = drop;
+            c.has_res = has_res; c.x_acc = x_has_skip; c.a1 = a1; c.raw = raw; c.a2 = a2; c.g1 = g1; c.b1 = b1; c.g2 = g2; c.b2 = b2; c.drop = drop; c.mr1 = mr1; c.mr2 = mr2;
             bwd_res_block(c);
         }
         return L.attn ? add_attention(L, y, raw_out) : y;      // (its backward is recorded after the block's: it runs first)
@@ -1036,8 +1040,9 @@ struct sr3_engine {
         bf16* O = static_cast<bf16*>(role("O", (size_t)Bp * HW * C * 2 * PW));
         Act y = new_act(C, Hh, Ww, L.name);
         add_prep(x, nullptr, gn_w, gn_b, G, false, n, nullptr);
+        float* mr_attn = last_mr;
         if (dry) {
-            if (train) { AttnBwdCtx c; c.p = p; c.x = x; c.y = y; c.C = C; c.Hh = Hh; c.Ww = Ww; c.Lt = Lt; c.per = per; c.nz = nz; c.n = n; c.qk = qk; c.vT = vT; c.P = P; c.O = O; c.gn_w = gn_w; c.gn_b = gn_b; bwd_attention(c); }
+            if (train) { AttnBwdCtx c; c.p = p; c.x = x; c.y = y; c.C = C; c.Hh = Hh; c.Ww = Ww; c.Lt = Lt; c.per = per; c.nz = nz; c.n = n; c.qk = qk; c.vT = vT; c.P = P; c.O = O; c.gn_w = gn_w; c.gn_b = gn_b; c.mr = mr_attn; bwd_attention(c); }
             return y;
         }
         const bool merged_qkv = (getenv("SR3_NO_MERGED_QKV") == nullptr || precise) && C % 128 == 0;     // whole 128-column tiles on either side of 2C
@@ -1108,7 +1113,7 @@ struct sr3_engine {
         }
         if (train) {
             AttnBwdCtx c; c.p = p; c.x = x; c.y = y; c.C = C; c.Hh = Hh; c.Ww = Ww; c.Lt = Lt; c.per = per; c.nz = nz; c.n = n; c.qk = qk; c.vT = vT; c.P = P; c.O = O;
-            c.gn_w = gn_w; c.gn_b = gn_b;
+            c.gn_w = gn_w; c.gn_b = gn_b; c.mr = mr_attn;
             bwd_attention(c);
         }
         return y;
@@ -1314,7 +1319,7 @@ struct sr3_engine {
             float* b = f32_param("final_conv.block.3.bias", {co});
             bf16* a = static_cast<bf16*>(role("a1", (size_t)Bp * H * W * C * 2 * PW));
             add_prep(x, nullptr, g, be, cfg.norm_groups, true, a, nullptr);
-            if (train) bwd_final(x, a, g, be);
+            if (train) bwd_final(x, a, g, be, last_mr);
             if (!dry) {
                 GemmDesc d; d.n_a = 1; d.a[0] = nhwc_src(a, Bp, H, W, C * PW);
                 add_conv_slabs(d.slabs, 0, C, 3, 1, 0);

@@ -285,6 +285,7 @@ struct GnBwdParams {
     int add_ld;
     float* dst0; int acc0; __nv_bfloat16* dst0_b; float* gsum0; int gsum_ld0;    // gradient of source 0: [B][HW][C0]; acc: dst += ; gsum[b * ld + c] += column sums
     float* dst1; int acc1; __nv_bfloat16* dst1_b; float* gsum1; int gsum_ld1;    // source 1 (skip connection)
+    const float* mr;         // [B][groups][2] (mean, rstd) saved by the forward's GroupNorm apply
     float* dgamma; float* dbeta; float gscale;   // pass 2, block (0, 0): dgamma[c] = gscale sum_b S2[b][c], dbeta[c] = gscale sum_b S1[b][c]
 };
 
@@ -335,7 +336,15 @@ __global__ void __launch_bounds__(512) gn_bwd_kernel(const GnBwdParams p) {
     float* m2 = m1 + f.groups;
     float* red = m2 + f.groups;                    // [2C]
     const int b = blockIdx.y;
-    groupnorm_mean_rstd(f, b, scratch, gm, gr);
+    if (p.mr != nullptr) {
+        for (int g = threadIdx.x; g < f.groups; g += blockDim.x) {
+            gm[g] = __ldcg(&p.mr[(static_cast<long long>(b) * f.groups + g) * 2]);
+            gr[g] = __ldcg(&p.mr[(static_cast<long long>(b) * f.groups + g) * 2 + 1]);
+        }
+        __syncthreads();
+    } else {
+        groupnorm_mean_rstd(f, b, scratch, gm, gr);
+    }
     if (APPLY) {
         if (blockIdx.x == 0 && blockIdx.y == 0 && (p.dgamma != nullptr || p.dbeta != nullptr)) {
             for (int c = threadIdx.x; c < C; c += blockDim.x) {
