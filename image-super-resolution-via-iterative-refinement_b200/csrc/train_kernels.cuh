@@ -89,7 +89,8 @@ struct WgradTap { int dchan, dw, p, dh; };
 struct WgradParams {
     CUtensorMap dy_map;      // 5-D bf16 (Cout, OW, 1, OH, B), box {64, 8, 1, 8, 1}
     CUtensorMap x_map;       // 5-D bf16 view of X, box {64, 8, 1, 8, 1}
-    float* ws;               // [slices][co_pad][ntaps][Cin]
+    float* ws;               // partial tiles: ws[slice * ws_slice_stride + co * ws_row_stride + tap * Cin + ci]  (default [slices][co_pad][ntaps][Cin])
+    long long ws_slice_stride, ws_row_stride;
     int Cin, co_pad, cout_valid, OH, OW, B;
     int ntaps, taps_per_cta;
     int patches;             // B * (OH/8) * (OW/8)
@@ -216,7 +217,7 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
                     for (int j = 0; j < 32; ++j) v[j] = 0u;
                 }
                 if (co >= p.cout_valid) continue;               // padded rows of the 128-row tile (Cout = 64 / 3): nobody reads them
-                float4* dst = reinterpret_cast<float4*>(p.ws + ((static_cast<long long>(slice) * p.co_pad + co) * p.ntaps + tap0 + t) * p.Cin + ci0 + ch * 32);
+                float4* dst = reinterpret_cast<float4*>(p.ws + slice * p.ws_slice_stride + co * p.ws_row_stride + static_cast<long long>(tap0 + t) * p.Cin + ci0 + ch * 32);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                     dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
@@ -669,7 +670,8 @@ __global__ void __launch_bounds__(256) bgemm_kernel(const BgemmParams p) {
         }
 }
 // softmax backward, in place on dP: dS = P * (dP - sum_k P dP) * scale; rows / segments as softmax_kernel
-__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, float* __restrict__ dP, long long rows, int L, int seg, float scale) {
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, float* __restrict__ dP, __nv_bfloat16* __restrict__ dS_b, long long rows, int L, int seg,
+                                                          float scale) {
     pdl_launch_dependents();
     pdl_wait();
     const long long row = blockIdx.x * static_cast<long long>(blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -682,7 +684,25 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const __nv_bfloat16* _
     for (int k = k0 + lane; k < k0 + seg; k += 32) dot += __bfloat162float(pr[k]) * d[k];
 #pragma unroll
     for (int o = 16; o; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
-    for (int k = lane; k < L; k += 32) d[k] = (k >= k0 && k < k0 + seg) ? __bfloat162float(pr[k]) * (d[k] - dot) * scale : 0.f;
+    for (int k = lane; k < L; k += 32) {
+        const float v = (k >= k0 && k < k0 + seg) ? __bfloat162float(pr[k]) * (d[k] - dot) * scale : 0.f;
+        d[k] = v;
+        if (dS_b) dS_b[row * L + k] = __float2bfloat16_rn(v);
+    }
+}
+// bf16 matrix transpose, batched: dst[z][c][r] = src[z][r * src_ld + c]  (r < R, c < Cc); one 32x32 tile per block
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int R, int Cc, long long src_ld,
+                                                             long long src_z, long long dst_z) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ __nv_bfloat16 t[32][33];
+    const int z = blockIdx.z, r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int i = ty; i < 32; i += 8)
+        if (r0 + i < R && c0 + tx < Cc) t[i][tx] = src[z * src_z + (r0 + i) * src_ld + c0 + tx];
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+        if (c0 + i < Cc && r0 + tx < R) dst[z * dst_z + static_cast<long long>(c0 + i) * R + r0 + tx] = t[tx][i];
 }
 // fp32 [rows][C] -> bf16 (gradient operands of the tile / wgrad kernels)
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n4) {
