@@ -35,6 +35,7 @@ _SIGS = {
     "sr3_train_num_backward_blocks": (c_int, [c_void_p]),
     "sr3_train_backward_begin": (c_int, [c_void_p, c_float, POINTER(c_void_p), c_int]),
     "sr3_train_backward_block": (c_int, [c_void_p, c_int, c_void_p]),
+    "sr3_train_backward_flush": (c_int, [c_void_p, c_void_p]),
     "sr3_train_backward_finish": (c_int, [c_void_p, c_void_p]),
     "sr3_train_block_params": (c_int, [c_void_p, c_int, POINTER(c_int), c_int, POINTER(c_int)]),
     "sr3_train_backward_profile": (c_int, [c_void_p, c_float, POINTER(c_void_p), c_int, POINTER(c_float), c_void_p]),
@@ -289,7 +290,7 @@ class Engine:
         ms = (c_float * 8)()
         with torch.cuda.device(self.device):
             _check(lib().sr3_train_backward_profile(self._h, float(grad_scale), arr, len(grads), ms, _stream()))
-        names = {0: "dgrad_tile_kernel", 1: "groupnorm_elementwise", 4: "other", 5: "wgrad_slice_reduce", 6: "wgrad", 7: "attention_gemms"}
+        names = {0: "dgrad_tile_kernel", 1: "groupnorm_elementwise", 3: "bookkeeping", 4: "other", 5: "wgrad_slice_reduce", 6: "wgrad", 7: "attention_backward"}
         return {names.get(k, str(k)): ms[k] for k in range(8) if ms[k] > 0}
 
     def num_backward_blocks(self):
@@ -302,6 +303,11 @@ class Engine:
     def backward_block(self, i):
         with torch.cuda.device(self.device):
             _check(lib().sr3_train_backward_block(self._h, int(i), _stream()))
+
+    def backward_flush(self):
+        """Sum the weight-gradient partial tiles of the layers run since the last flush (one launch); call before all-reducing a bucket."""
+        with torch.cuda.device(self.device):
+            _check(lib().sr3_train_backward_flush(self._h, _stream()))
 
     def backward_finish(self):
         with torch.cuda.device(self.device):

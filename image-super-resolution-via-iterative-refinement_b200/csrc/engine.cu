@@ -1572,6 +1572,15 @@ int sr3_train_backward_block(sr3_engine* e, int block, void* stream) {
     e->train_backward_block(block, static_cast<cudaStream_t>(stream));
     API_END
 }
+/* Reduce the weight-gradient partial tiles of the layers run since the last flush (one launch): call it before handing a finished bucket of
+ * gradients to the all-reduce.  sr3_train_backward / _finish flush what is left themselves. */
+int sr3_train_backward_flush(sr3_engine* e, void* stream) {
+    API_BEGIN
+    REQUIRE(e && !e->grad_dst.empty(), "sr3_train_backward_begin has not been called");
+    CK(cudaSetDevice(e->dev));
+    e->reduce_flush(static_cast<cudaStream_t>(stream));
+    API_END
+}
 int sr3_train_backward_finish(sr3_engine* e, void* stream) {
     API_BEGIN
     REQUIRE(e && !e->grad_dst.empty(), "sr3_train_backward_begin has not been called");
@@ -1595,12 +1604,17 @@ int sr3_train_backward_profile(sr3_engine* e, float grad_scale, float* const* gr
     CK(cudaSetDevice(e->dev));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     e->train_backward_begin(grad_scale, grads);
+    e->reduce_prepare(st); e->reduce_begun = true;
     std::vector<cudaEvent_t> evs;
     std::vector<int> kinds;
     auto mark = [&]() { cudaEvent_t ev; CK(cudaEventCreate(&ev)); CK(cudaEventRecord(ev, st)); evs.push_back(ev); };
     mark();
-    for (size_t i = e->bwd_blocks.size(); i-- > 0;)
+    int blocks_since_flush = 0;
+    for (size_t i = e->bwd_blocks.size(); i-- > 0;) {
         for (size_t j = 0; j < e->bwd_blocks[i].size(); ++j) { e->bwd_blocks[i][j](st); kinds.push_back(e->bwd_kinds[i][j]); mark(); }
+        if (++blocks_since_flush == 6) { e->reduce_flush(st); kinds.push_back(5); mark(); blocks_since_flush = 0; }     // about one flush per gradient bucket
+    }
+    e->reduce_flush(st); kinds.push_back(5); mark();
     e->bwd_film_and_embed(st); kinds.push_back(4); mark();
     CK(cudaStreamSynchronize(st));
     for (int k = 0; k < 8; ++k) ms_by_kind[k] = 0.f;

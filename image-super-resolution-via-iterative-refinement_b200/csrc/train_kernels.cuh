@@ -235,35 +235,53 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 // loads in flight), the partial sums meet in shared memory laid out [ci][tap] = the OIHW order, are added in warp order (deterministic) and
 // written as one contiguous span.  (Finalising inside wgrad_kernel by the last-arriving CTA of a tile was measured slower: its 4-byte stores
 // at a 36-byte stride and the serial tail cost more than the launch they save.)
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ grad, int slices, int co_pad, int ntaps, int Cin,
-                                                           int cout_valid, int cin_valid, float gscale, int sw) {
+// Table-driven: ONE launch reduces the partial tiles of every weight-gradient kernel that ran since the last flush (the layers of a gradient
+// bucket): blocks find their entry by its block-offset range.
+struct WgradReduceDesc {
+    const float* ws; float* grad;
+    int slices, co_pad, ntaps, Cin, cout_valid, cin_valid, sw, blocks_x;
+    int block_begin, block_end;            // this entry's blocks inside the flush it belongs to are [block_begin, block_end) minus the flush's first block
+};
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ tab, int first, int count, int block_base, float gscale) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sm[8][32 * WGRAD_MAX_TAPS];
+    __shared__ int s_entry;
+    if (threadIdx.x == 0) {
+        const int gb = block_base + blockIdx.x;
+        int e = first;
+        for (int i = 0; i < count; ++i)
+            if (gb >= tab[first + i].block_begin && gb < tab[first + i].block_end) { e = first + i; break; }
+        s_entry = e;
+    }
+    __syncthreads();
+    const WgradReduceDesc d = tab[s_entry];
+    const int lb = block_base + blockIdx.x - d.block_begin;
+    const int bx = lb % d.blocks_x, co = lb / d.blocks_x;
+    const int sw = d.sw, ntaps = d.ntaps;
     const int groups = 8 / sw;                       // 32-channel groups per block
-    const int co = blockIdx.y;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int grp = w / sw, sl = w % sw;
-    const int ci0 = blockIdx.x * 32 * groups;
+    const int ci0 = bx * 32 * groups;
     const int ci = ci0 + grp * 32 + lane;
-    const long long sstride = static_cast<long long>(co_pad) * ntaps * Cin;
+    const long long sstride = static_cast<long long>(d.co_pad) * ntaps * d.Cin;
     float acc[WGRAD_MAX_TAPS];
 #pragma unroll
     for (int t = 0; t < WGRAD_MAX_TAPS; ++t) acc[t] = 0.f;
-    if (ci < cin_valid) {
-        const float* s = ws + static_cast<long long>(co) * ntaps * Cin + ci;
-        for (int k = sl; k < slices; k += sw) {
+    if (ci < d.cin_valid) {
+        const float* s = d.ws + static_cast<long long>(co) * ntaps * d.Cin + ci;
+        for (int k = sl; k < d.slices; k += sw) {
 #pragma unroll
             for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
-                if (t < ntaps) acc[t] += __ldcg(&s[k * sstride + static_cast<long long>(t) * Cin]);
+                if (t < ntaps) acc[t] += __ldcg(&s[k * sstride + static_cast<long long>(t) * d.Cin]);
         }
     }
 #pragma unroll
     for (int t = 0; t < WGRAD_MAX_TAPS; ++t)
         if (t < ntaps) sm[w][lane * ntaps + t] = acc[t];
     __syncthreads();
-    const int nci = min(32 * groups, cin_valid - ci0);
-    float* g = grad + (static_cast<long long>(co) * cin_valid + ci0) * ntaps;
+    const int nci = min(32 * groups, d.cin_valid - ci0);
+    float* g = d.grad + (static_cast<long long>(co) * d.cin_valid + ci0) * ntaps;
     for (int i = threadIdx.x; i < nci * ntaps; i += blockDim.x) {
         const int gi = i / (32 * ntaps), r = i - gi * 32 * ntaps;      // channel group, position inside its [32][ntaps] slab
         float a = 0.f;

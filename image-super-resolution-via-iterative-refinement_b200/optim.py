@@ -12,6 +12,7 @@ class FusedAdam(torch.optim.Optimizer):
         if weight_decay != 0:
             raise NotImplementedError("FusedAdam: weight_decay is not used by the reference and not implemented")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        self._tables = {}
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=1.0):
@@ -21,22 +22,29 @@ class FusedAdam(torch.optim.Optimizer):
             ps = [p for p in group["params"] if p.grad is not None]
             if not ps:
                 continue
-            st = self.state.setdefault("_fused_%d" % id(group), {"step": 0})
-            st["step"] += 1
-            rows = np.empty((len(ps), 5), dtype=np.int64)
-            for i, p in enumerate(ps):
+            st = self._tables.setdefault(id(group), {})       # device table cache: not part of the optimizer's state_dict
+            group["step"] = int(group.get("step", 0)) + 1    # saved / restored with the param group (bias correction survives a resume)
+            for p in ps:
                 s = self.state[p]
                 if not s:
                     s["exp_avg"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
                     s["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-                g = p.grad
-                if not (p.is_cuda and p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32):
-                    raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
-                rows[i] = (p.data_ptr(), g.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr(), p.numel())
+            # the device table is rebuilt (one synchronous H2D copy, which would also drain the GPU queue) only when a tensor moved: with
+            # gradients that live in a fixed arena (parallel.GradientBuckets) that is once
+            key = tuple((p.data_ptr(), p.grad.data_ptr()) for p in ps)
+            if st.get("key") != key:
+                rows = np.empty((len(ps), 5), dtype=np.int64)
+                for i, p in enumerate(ps):
+                    s, g = self.state[p], p.grad
+                    if not (p.is_cuda and p.is_contiguous() and g.is_contiguous() and p.dtype == torch.float32 and g.dtype == torch.float32):
+                        raise RuntimeError("FusedAdam needs contiguous fp32 CUDA parameters and gradients")
+                    rows[i] = (p.data_ptr(), g.data_ptr(), s["exp_avg"].data_ptr(), s["exp_avg_sq"].data_ptr(), p.numel())
+                st["table"] = torch.from_numpy(rows).to(ps[0].device)
+                st["key"] = key
             dev = ps[0].device
-            table = torch.from_numpy(rows).to(dev, non_blocking=False)
+            table = st["table"]
             with torch.cuda.device(dev):
-                _native.adam_step(table, len(ps), group["lr"], group["betas"][0], group["betas"][1], group["eps"], st["step"], grad_scale)
+                _native.adam_step(table, len(ps), group["lr"], group["betas"][0], group["betas"][1], group["eps"], group["step"], grad_scale)
             self._bump(ps)
         return None
 

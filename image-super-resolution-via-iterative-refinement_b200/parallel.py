@@ -220,9 +220,12 @@ class DataParallelTrainer:
         bk = self.buckets
         eng.backward_begin(1.0 / float(gb * c * h * w), bk.views)
         bk.begin()
+        boundaries = {fb for fb, _, _ in bk.slices}
         for i in range(eng.num_backward_blocks() - 1, -1, -1):
             eng.backward_block(i)
-            bk.ready(i)
+            if i in boundaries:
+                eng.backward_flush()             # the bucket's conv weight gradients: partial tiles -> OIHW, one launch
+                bk.ready(i)
         eng.backward_finish()
         bk.finish()
         self.opt.step()

@@ -112,10 +112,13 @@ int sr3_train_forward(sr3_engine* e, const float* hr, const float* sr, const flo
 int sr3_train_backward(sr3_engine* e, float grad_scale, float* const* grads, int n_grads, void* stream);
 /* The same backward layer by layer, so that the caller can overlap the gradient all-reduce (training row) with the layers still to
  * come: begin -> block n-1, n-2, ..., 0 -> finish (FiLM projections + noise-level MLP).  sr3_train_block_params lists the parameters whose
- * gradient is final once `block` has run (the rest -- noise_func / block1 conv bias / noise_level_mlp -- are final after finish). */
+ * gradient is final once `block` has run AND sr3_train_backward_flush has been called (conv weight gradients leave the tensor-core kernel as
+ * per-slice partial tiles; one table-driven launch per flush sums them) -- the rest (noise_func / block1 conv bias / noise_level_mlp) are
+ * final after finish. */
 int sr3_train_num_backward_blocks(const sr3_engine* e);
 int sr3_train_backward_begin(sr3_engine* e, float grad_scale, float* const* grads, int n_grads);
 int sr3_train_backward_block(sr3_engine* e, int block, void* stream);
+int sr3_train_backward_flush(sr3_engine* e, void* stream);    /* reduce the weight-gradient partial tiles produced since the last flush (one launch) */
 int sr3_train_backward_finish(sr3_engine* e, void* stream);
 int sr3_train_block_params(const sr3_engine* e, int block, int* indices, int cap, int* n);
 /* Profiling: the whole backward with CUDA events around every op; ms_by_kind[8]: device time per op kind (0 data-gradient tile kernel,
