@@ -15,10 +15,10 @@ def make_opt(unet, image_size, conditional=True, phase="train", sched=SCHED):
                       "diffusion": {"image_size": image_size, "channels": 3, "conditional": conditional}}}
 
 
-def build_train_net(unet, image_size, seed, loss_type="l1", sched=SCHED):
+def build_train_net(unet, image_size, seed, loss_type="l1", sched=SCHED, conditional=True):
     import sr3_b200
     torch.manual_seed(seed)
-    net = sr3_b200.define_G(make_opt(unet, image_size, True, "train", sched)).cuda()      # phase 'train': orthogonal init (networks.py:110-112)
+    net = sr3_b200.define_G(make_opt(unet, image_size, conditional, "train", sched)).cuda()      # phase 'train': orthogonal init (networks.py:110-112)
     net.loss_type = loss_type
     net.set_loss("cuda")
     net.set_new_noise_schedule(sched, "cuda")
@@ -55,7 +55,8 @@ def ours_loss_and_grads(net, hr, sr, gamma, noise, train_mode=False, dropout_see
     for p in net.parameters():
         p.grad = None
     b, c, h, w = hr.shape
-    l = net.p_losses({"HR": hr.cuda(), "SR": sr.cuda()}, noise=noise.cuda(), gamma=gamma, dropout_seed=dropout_seed)
+    x_in = {"HR": hr.cuda(), "SR": sr.cuda()} if net.conditional else {"HR": hr.cuda()}
+    l = net.p_losses(x_in, noise=noise.cuda(), gamma=gamma, dropout_seed=dropout_seed)
     (l.sum() / int(b * c * h * w)).backward()
     grads = {k[len("denoise_fn."):]: p.grad.detach().clone() for k, p in net.named_parameters()}
     return float(l.item()), grads
@@ -65,7 +66,7 @@ def oracle_loss_and_grads(net, unet, image_size, hr, sr, gamma, noise, loss_type
     cfg = oracle_cfg(unet, image_size)
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.denoise_fn.state_dict().items()}
     sch = orc.make_schedule(SCHED)
-    loss = orc.train_loss(sd, cfg, sch, hr, sr, gamma, noise, loss_type, dropout_masks)
+    loss = orc.train_loss(sd, cfg, sch, hr, sr if net.conditional else None, gamma, noise, loss_type, dropout_masks)
     loss.backward()
     b, c, h, w = hr.shape
     return float(loss.item()) * b * c * h * w, {k: v.grad for k, v in sd.items()}

@@ -40,6 +40,19 @@ def test_gradients_match_oracle_l2(name, unet, R, B):
         assert e < GRAD_TOL, (n, e, c)
 
 
+def test_gradients_unconditional_model():
+    """sample_sr3_128.json-style model (in_channel 3, no condition image: diffusion.py:238-241 feeds x_noisy alone)."""
+    unet = dict(TINY, in_channel=3)
+    net = tu.build_train_net(unet, 32, 5, "l2", conditional=False)
+    hr, sr, noise = tu.batch(2, 32, 1000)
+    gamma = tu.draw_gamma(2, 7)
+    lo, go = tu.ours_loss_and_grads(net, hr, sr, gamma, noise)
+    lr_, gr = tu.oracle_loss_and_grads(net, unet, 32, hr, sr, gamma, noise, "l2")
+    assert abs(lo - lr_) / abs(lr_) < 1e-2, (lo, lr_)
+    for n, e, c, _ in tu.compare(go, gr):
+        assert e < GRAD_TOL, (n, e, c)
+
+
 def test_gradients_l1_and_reference_optimize_parameters_semantics(train_golden):
     """The loss the reference trains with (L1, sum / (b c h w)): loss value within 1e-2 of the golden, gradients of all parameters close in
     direction to the golden ones (signatures: norms and samples recorded from the unmodified reference)."""
