@@ -694,7 +694,7 @@ struct sr3_engine {
     // single-launch re-pack (bf16 precision): one PackDesc per packed copy, its source = parameter `pack_src[i]` (second source of a fused
     // bias: `pack_src2[i]`); device table rebuilt only when the parameter pointers change
     std::vector<PackDesc> pack_descs; std::vector<int> pack_src, pack_src2;
-    PackDesc* pack_dev = nullptr; std::vector<const float*> pack_last_ptrs;
+    PackDesc* pack_dev = nullptr; int* pack_ends_dev = nullptr; int pack_blocks = 0; std::vector<const float*> pack_last_ptrs;
     void add_pack(const std::string& pname, PackDesc d, const std::string& pname2 = "") {
         if (dry || precise) return;
         pack_descs.push_back(d); pack_src.push_back(pindex.at(pname)); pack_src2.push_back(pname2.empty() ? -1 : pindex.at(pname2));
@@ -1690,12 +1690,35 @@ int sr3_engine_load_all_params(sr3_engine* e, const float* const* srcs, int n, v
         if (e->pack_last_ptrs.size() != (size_t)n || memcmp(e->pack_last_ptrs.data(), srcs, n * sizeof(float*)) != 0 || !e->pack_dev) {
             std::vector<PackDesc> tab = e->pack_descs;
             for (size_t i = 0; i < nd; ++i) { tab[i].src = srcs[e->pack_src[i]]; tab[i].src2 = e->pack_src2[i] >= 0 ? srcs[e->pack_src2[i]] : nullptr; }
-            if (!e->pack_dev) e->pack_dev = static_cast<PackDesc*>(e->mem.alloc(nd * sizeof(PackDesc)));
+            if (!e->pack_dev) {
+                e->pack_dev = static_cast<PackDesc*>(e->mem.alloc(nd * sizeof(PackDesc)));
+                e->pack_ends_dev = static_cast<int*>(e->mem.alloc(nd * sizeof(int)));
+                // blocks in proportion to the work of an entry: ~8 (o, c) pairs (x k*k taps) or 32 plain elements per thread
+                std::vector<int> ends(nd);
+                int acc = 0;
+                for (size_t i = 0; i < nd; ++i) {
+                    const PackDesc& d = tab[i];
+                    long long items;
+                    switch (d.type) {
+                        case 0: case 6: items = (d.n + 3) / 4; break;
+                        case 1: case 2: items = 1LL * d.Cout * d.Cin; break;
+                        case 3: items = 2LL * d.Cin * d.Cout; break;
+                        case 4: items = 4LL * d.Cin * d.Cout; break;
+                        default: items = 4LL * d.Cin * d.Cout; break;
+                    }
+                    long long nb = (items + 256 * 8 - 1) / (256 * 8);
+                    if (nb < 1) nb = 1;
+                    if (nb > 4096) nb = 4096;
+                    acc += (int)nb; ends[i] = acc;
+                }
+                e->pack_blocks = acc;
+                CK(cudaMemcpy(e->pack_ends_dev, ends.data(), nd * sizeof(int), cudaMemcpyHostToDevice));
+            }
             CK(cudaMemcpyAsync(e->pack_dev, tab.data(), nd * sizeof(PackDesc), cudaMemcpyHostToDevice, st));
             CK(cudaStreamSynchronize(st));                 // `tab` is pageable host memory
             e->pack_last_ptrs.assign(srcs, srcs + n);
         }
-        pack_all_kernel<<<dim3(32, (unsigned)std::min<size_t>(nd, 65535)), 256, 0, st>>>(e->pack_dev, (int)nd);
+        pack_all_kernel<<<dim3((unsigned)e->pack_blocks), 256, 0, st>>>(e->pack_dev, e->pack_ends_dev, (int)nd);
         CK(cudaGetLastError());
         for (auto& p : e->params) p.loaded = true;
         return 0;

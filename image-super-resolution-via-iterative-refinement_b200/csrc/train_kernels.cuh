@@ -235,6 +235,15 @@ __global__ void __launch_bounds__(WGRAD_THREADS, 1) wgrad_kernel(const __grid_co
 // loads in flight), the partial sums meet in shared memory laid out [ci][tap] = the OIHW order, are added in warp order (deterministic) and
 // written as one contiguous span.  (Finalising inside wgrad_kernel by the last-arriving CTA of a tile was measured slower: its 4-byte stores
 // at a 36-byte stride and the serial tail cost more than the launch they save.)
+// first index i in [0, n) with ends[i] > b  (ends ascending): which table entry owns block b
+__device__ __forceinline__ int find_entry(const int* __restrict__ ends, int n, int b) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(&ends[mid]) > b) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
 // Table-driven: ONE launch reduces the partial tiles of every weight-gradient kernel that ran since the last flush (the layers of a gradient
 // bucket): blocks find their entry by its block-offset range.
 struct WgradReduceDesc {
@@ -242,20 +251,12 @@ struct WgradReduceDesc {
     int slices, co_pad, ntaps, Cin, cout_valid, cin_valid, sw, blocks_x;
     int block_begin, block_end;            // this entry's blocks inside the flush it belongs to are [block_begin, block_end) minus the flush's first block
 };
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ tab, int first, int count, int block_base, float gscale) {
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceDesc* __restrict__ tab, const int* __restrict__ block_ends, int first, int count, int block_base,
+                                                           float gscale) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sm[8][32 * WGRAD_MAX_TAPS];
-    __shared__ int s_entry;
-    if (threadIdx.x == 0) {
-        const int gb = block_base + blockIdx.x;
-        int e = first;
-        for (int i = 0; i < count; ++i)
-            if (gb >= tab[first + i].block_begin && gb < tab[first + i].block_end) { e = first + i; break; }
-        s_entry = e;
-    }
-    __syncthreads();
-    const WgradReduceDesc d = tab[s_entry];
+    const WgradReduceDesc d = tab[first + find_entry(block_ends + first, count, block_base + blockIdx.x)];
     const int lb = block_base + blockIdx.x - d.block_begin;
     const int bx = lb % d.blocks_x, co = lb / d.blocks_x;
     const int sw = d.sw, ntaps = d.ntaps;
@@ -888,11 +889,12 @@ __device__ __forceinline__ void pack_entry(const PackDesc& d, long long i0, long
     default: break;
     }
 }
-__global__ void __launch_bounds__(256) pack_all_kernel(const PackDesc* __restrict__ tab, int n_entries) {
-    for (int e = blockIdx.y; e < n_entries; e += gridDim.y) {
-        const PackDesc d = tab[e];
-        pack_entry(d, blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x, static_cast<long long>(gridDim.x) * blockDim.x);
-    }
+// block_ends[e] = one past the last block of entry e (blocks are dealt in proportion to the entries' work)
+__global__ void __launch_bounds__(256) pack_all_kernel(const PackDesc* __restrict__ tab, const int* __restrict__ block_ends, int n_entries) {
+    const int e = find_entry(block_ends, n_entries, blockIdx.x);
+    const int b0 = e == 0 ? 0 : __ldg(&block_ends[e - 1]), nb = __ldg(&block_ends[e]) - b0;
+    const PackDesc d = tab[e];
+    pack_entry(d, (blockIdx.x - b0) * static_cast<long long>(blockDim.x) + threadIdx.x, static_cast<long long>(nb) * blockDim.x);
 }
 
 }  // namespace sr3
