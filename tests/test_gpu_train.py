@@ -157,3 +157,22 @@ def test_three_adam_steps_reference_wrapper_flow(train_golden):
             moved += 1
             assert (d_ours - d_ref).norm() <= 0.5 * d_ref.norm() + 1e-7, (k, d_ours, d_ref)
     assert moved > 50
+
+
+def test_fused_adam_matches_torch_adam():
+    """sr3_b200.FusedAdam (one native launch over a device table of tensors) against torch.optim.Adam with the reference's settings
+    (model/model.py:39-40: lr from the config, torch defaults otherwise), five steps on tensors of assorted shapes."""
+    import sr3_b200
+    g = torch.Generator().manual_seed(0)
+    shapes = [(64, 6, 3, 3), (64,), (128, 64, 3, 3), (256, 64), (3, 64, 3, 3), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, generator=g).cuda()) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa, ob = sr3_b200.FusedAdam(pa, lr=1e-4), torch.optim.Adam(pb, lr=1e-4)
+    for step in range(5):
+        for x, y in zip(pa, pb):
+            gr = torch.randn(x.shape, generator=g).cuda() * (10.0 ** (step - 2))
+            x.grad, y.grad = gr.clone(), gr.clone()
+        oa.step(); ob.step()
+    for x, y in zip(pa, pb):
+        assert torch.allclose(x, y, rtol=1e-5, atol=1e-7), (x.shape, (x - y).abs().max().item())
+    assert oa.state_dict()["param_groups"][0]["step"] == 5
