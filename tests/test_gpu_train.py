@@ -40,6 +40,26 @@ def test_gradients_match_oracle_l2(name, unet, R, B):
         assert e < GRAD_TOL, (n, e, c)
 
 
+@pytest.mark.timeout(900)
+def test_gradients_full_16_128_config():
+    """sr_sr3_16_128.json (five levels 128..8, two ResnetBlocks per level, attention at 16x16 and in the middle block, 97.8 M parameters), two
+    images: the gradient of every one of the 362 parameter tensors against the oracle's fp32 autograd."""
+    full = dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.0)
+    net = tu.build_train_net(full, 128, 5, "l2")
+    hr, sr, noise = tu.batch(2, 128, 1000)
+    gamma = tu.draw_gamma(2, 7)
+    lo, go = tu.ours_loss_and_grads(net, hr, sr, gamma, noise)
+    torch.set_num_threads(min(16, torch.get_num_threads()))
+    lr_, gr = tu.oracle_loss_and_grads(net, full, 128, hr, sr, gamma, noise, "l2")
+    assert abs(lo - lr_) / abs(lr_) < 1e-2, (lo, lr_)
+    rows = tu.compare(go, gr)
+    assert len(rows) == 362
+    worst = sorted(rows, key=lambda r: -r[1])[:8]
+    print("worst:", [(n, f"{e:.2e}", f"{c:.5f}") for n, e, c, _ in worst])
+    bad = [(n, e, c) for n, e, c, _ in rows if e >= 3e-2]
+    assert not bad, bad[:10]
+
+
 def test_gradients_unconditional_model():
     """sample_sr3_128.json-style model (in_channel 3, no condition image: diffusion.py:238-241 feeds x_noisy alone)."""
     unet = dict(TINY, in_channel=3)

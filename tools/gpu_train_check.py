@@ -10,6 +10,7 @@ import _train_util as tu
 
 CFGS = {
     "tiny": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2], attn_res=[16], res_blocks=1, dropout=0.0), 32, 2),
+    "full": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 4, 8, 8], attn_res=[16], res_blocks=2, dropout=0.0), 128, 2),
     "three": (dict(in_channel=6, out_channel=3, inner_channel=64, channel_multiplier=[1, 2, 2], attn_res=[8], res_blocks=1, dropout=0.0), 32, 3),
 }
 
