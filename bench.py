@@ -358,6 +358,85 @@ def time_training(dev, per_batch, global_batch, K, W, barrier, dist_mod=None, ho
     return float(t_ms.item()) / K, comm_ms, losses, n_blocks, n_buckets
 
 
+def cpu_train_baseline(steps=2, sample_batch=2, global_batch=64):
+    """The unmodified reference's optimize_parameters arithmetic (model/model.py:48-58: netG(data) -> sum / (b c h w) -> backward -> Adam) on the
+    host cores, on a bounded sample: `sample_batch` images of the global batch per iteration (fp32, torch-CPU); the per-image cost is linear in the
+    batch, so steps/s at the global batch = 1 / (seconds per sample iteration * global_batch / sample_batch)."""
+    import torch
+    ref_root = os.path.join(ROOT, "oracle", "_ref")
+    kind = "port"
+    torch.manual_seed(0)
+    g = torch.Generator().manual_seed(5)
+    hr = torch.rand(sample_batch, 3, IMAGE, IMAGE, generator=g) * 2 - 1
+    sr = torch.rand(sample_batch, 3, IMAGE, IMAGE, generator=g) * 2 - 1
+    n = os.cpu_count() or 1
+    threads = min(n, 32)
+    torch.set_num_threads(threads)
+    net = None
+    if os.path.exists(os.path.join(ref_root, "model", "networks.py")):
+        try:
+            sys.path.insert(0, ref_root)
+            import importlib
+            networks = importlib.import_module("model.networks")
+            opt = make_opt(SCHED)
+            opt["phase"] = "train"
+            opt["gpu_ids"] = None
+            net = networks.define_G(opt)
+            net.set_loss("cpu")
+            net.set_new_noise_schedule(SCHED, "cpu")
+            net.train()
+            kind = "reference"
+        except Exception as e:
+            print(f"bench.py: oracle/_ref unusable for the training baseline ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
+            net = None
+        finally:
+            if sys.path and sys.path[0] == ref_root:
+                sys.path.pop(0)
+    ts = []
+    if net is not None:
+        optim = torch.optim.Adam(list(net.parameters()), lr=1e-4)
+        for i in range(steps + 1):
+            t0 = time.perf_counter()
+            optim.zero_grad()
+            l = net({"HR": hr, "SR": sr})
+            (l.sum() / hr.numel()).backward()
+            optim.step()
+            if i > 0:
+                ts.append(time.perf_counter() - t0)
+    else:
+        import numpy as np
+        from oracle import sr3_oracle as orc
+        cfg = orc.UNetConfig(6, 3, 64, 32, (1, 2, 4, 8, 8), (16,), 2, 0.2, 128)
+        sd = orc.init_state_dict(cfg, 0, orthogonal=True)
+        sch = orc.make_schedule(SCHED)
+        optim = orc.make_adam(sd, 1e-4)
+        for i in range(steps + 1):
+            t0 = time.perf_counter()
+            _, gamma = orc.draw_gamma(sch, sample_batch, np.random.RandomState(i))
+            orc.train_step(sd, optim, cfg, sch, hr, sr, gamma, torch.randn(hr.shape))
+            if i > 0:
+                ts.append(time.perf_counter() - t0)
+    per = sum(ts) / len(ts)
+    scale = global_batch / sample_batch
+    return {"value": 1.0 / (per * scale), "unit": "steps/s", "cores": threads, "kind": kind, "host_cores": n,
+            "sample": f"optimize_parameters arithmetic on {sample_batch} of the {global_batch} images per iteration ({steps} iterations after 1 warm-up, fp32 torch-CPU, "
+                      f"{per:.2f} s each), scaled by {scale:g} to the global batch", "seconds_per_sample_iteration": per}
+
+
+def run_reference_train(args, rank, world):
+    if rank != 0:
+        return
+    cb = cpu_train_baseline(steps=min(max(args.steps, 1), 3), global_batch=args.train_batch)
+    v = cb["value"]
+    line = {"impl": "reference", "metric": "training steps/sec (sr_sr3_16_128 fwd+bwd+Adam, global batch %d)" % args.train_batch, "value": v, "unit": "steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": "sr_sr3_16_128.json training step on host cores (bounded sample, see cpu_baseline.sample)",
+                                                             "global_batch": args.train_batch},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
+            "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
 def run_train(args, rank, local, world):
     """--workload train: BASELINE.json configs[3] -- sr_sr3_16_128.json training step (fwd + bwd + Adam), global batch 64, data parallel."""
     if world > 1:
@@ -386,6 +465,13 @@ def run_train(args, rank, local, world):
     with ClockSampler(local) as clk:
         ms, comm_ms, losses, n_blocks, n_buckets = time_training(dev, per, GB, K, W, barrier, dd, host_inputs=False)
     e2e_ms, _, _, _, _ = time_training(dev, per, GB, max(3, K // 2), 3, barrier, dd, host_inputs=True)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cb = cpu_train_baseline(steps=2, global_batch=GB)
+            cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")}
+        except Exception as e:
+            cpu = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         peaks = measured_peaks()
         fl = 3.0 * algorithmic_flops_per_image() * GB          # fwd + dgrad + wgrad (277 GFLOP per image)
@@ -404,7 +490,7 @@ def run_train(args, rank, local, world):
                 "roofline": {"bound": "tensor", "kernel": "whole training step (forward tile kernel + data-gradient tile kernel + wgrad_kernel)", "achieved": fl / world / (ms * 1e-3) / 1e12,
                              "peak": peaks["burst"], "unit": "TFLOP/s", "frac": fl / world / (ms * 1e-3) / 1e12 / peaks["burst"], "traffic": None,
                              "algorithmic_flops_per_step_per_gpu": fl / world, "peak_source": peaks["src"]},
-                "cpu_baseline": None, "losses_first_last": [losses[0], losses[-1]]}
+                "cpu_baseline": cpu, "losses_first_last": [losses[0], losses[-1]]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -430,7 +516,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference_train(args, rank, world) if args.workload == "train" else run_reference(args, rank, world)
     if args.workload == "train":
         return run_train(args, rank, local, world)
 
