@@ -494,15 +494,6 @@ __global__ void __launch_bounds__(512) gn_bwd_kernel(const GnBwdParams p) {
     }
 }
 
-// dgamma[c] = gscale * sum_b S2[b][c],  dbeta[c] = gscale * sum_b S1[b][c]
-__global__ void __launch_bounds__(256) gn_param_grad_kernel(const float* __restrict__ sums, float* __restrict__ dgamma, float* __restrict__ dbeta, int B, int C, float gscale) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    float a = 0.f, q = 0.f;
-    for (int b = 0; b < B; ++b) { a += sums[(static_cast<long long>(b) * C + c) * 2]; q += sums[(static_cast<long long>(b) * C + c) * 2 + 1]; }
-    if (dgamma) dgamma[c] = q * gscale;
-    if (dbeta) dbeta[c] = a * gscale;
-}
 // bias gradient from per-image channel sums: db[c] = gscale * sum_b gsum[b * ld + c]   (up to two destinations share it: conv2 + shortcut conv)
 __global__ void __launch_bounds__(256) bias_grad_kernel(const float* __restrict__ gsum, int ld, float* __restrict__ d0, float* __restrict__ d1, int B, int C, float gscale) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
