@@ -138,7 +138,7 @@ def test_philox_dropout_is_deterministic_and_has_the_right_rate():
     # gradient operand amplifies a perturbation d to ~2^-4 sqrt(d), so after a few layers two runs differ by the bf16 noise floor (2^-8).
     worst = sorted(((tu.rel(g1[k], g2[k]), k, float(g1[k].norm())) for k in g1), reverse=True)[:5]
     print("run-to-run:", worst)
-    assert l1 == l2 and worst[0][0] < 1e-2, worst
+    assert l1 == l2 and worst[0][0] < 2e-2, worst
     assert l1 != l3
     # the masks drop ~20 % of block2's activations: the loss differs from the eval-mode loss
     l0, _ = tu.ours_loss_and_grads(net, hr, sr, gamma, noise, train_mode=False)
