@@ -75,24 +75,13 @@ struct PrepParams {
 __device__ __forceinline__ void groupnorm_scale_shift(const PrepParams& p, int b, float* sc, float* sh, float* gm, float* gr) {
     const int C = p.C0 + p.C1;
     const int gs = C / p.groups;
-    // pass 1: the (sum, sumsq) pairs, as fp64, into registers -> group partials via shared memory.  The [2C]-float sc/sh area holds C
-    // doubles: first all the sums, then (after the group means are known) all the sums of squares.
+    // The [2C]-float sc/sh area holds C doubles: first all the sums, then (after the group means are known) all the sums of squares.  The two
+    // rounds re-read the statistics from L2 instead of caching (sum, sumsq) pairs in registers: the streaming loop that follows decides the
+    // kernel's register count, and 40 extra registers here cost the 128x128-level launches a third of their resident blocks (24 vs 15 us).
     double* scratch = reinterpret_cast<double*>(sc);
-    constexpr int MAXC = 10;                             // channels per thread: C <= 10 * blockDim.x (3072 channels at 320 threads)
-    double2 mine[MAXC];
-    int nmine = 0;
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k) {
-        const int c = threadIdx.x + k * blockDim.x;
-        if (c >= C) break;
-        mine[k] = (c < p.C0) ? __ldcg(reinterpret_cast<const double2*>(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2))
-                                     : __ldcg(reinterpret_cast<const double2*>(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2));
-        nmine = k + 1;
-    }
     const double inv = 1.0 / (static_cast<double>(gs) * static_cast<double>(p.HW));
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k)
-        if (k < nmine) scratch[threadIdx.x + k * blockDim.x] = mine[k].x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        scratch[c] = (c < p.C0) ? __ldcg(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2) : __ldcg(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2);
     __syncthreads();
     double gmean = 0.0;
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {        // groups <= blockDim.x: one iteration
@@ -101,9 +90,8 @@ __device__ __forceinline__ void groupnorm_scale_shift(const PrepParams& p, int b
         gmean = s * inv;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < MAXC; ++k)
-        if (k < nmine) scratch[threadIdx.x + k * blockDim.x] = mine[k].y;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+        scratch[c] = (c < p.C0) ? __ldcg(p.st0 + (static_cast<long long>(b) * p.C0 + c) * 2 + 1) : __ldcg(p.st1 + (static_cast<long long>(b) * p.C1 + (c - p.C0)) * 2 + 1);
     __syncthreads();
     for (int g = threadIdx.x; g < p.groups; g += blockDim.x) {
         double q = 0.0;
@@ -124,6 +112,8 @@ __device__ __forceinline__ void groupnorm_scale_shift(const PrepParams& p, int b
 
 // Block size = (C/4) * k threads: every thread owns ONE 4-channel column for the whole kernel (scale / shift live in
 // registers, no shared-memory or integer-division traffic in the streaming loop) and walks pixels k at a time.
+// DROP: training-mode forward of a block2 (Dropout after the SiLU); a separate instantiation keeps the Philox code out of the sampler's kernel
+template <bool DROP>
 __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
     pdl_launch_dependents();
     pdl_wait();
@@ -168,7 +158,7 @@ __global__ void __launch_bounds__(512) prep_kernel(const PrepParams p) {
             if (pp < pix1) {
                 float y0 = x[u].x * k4[0] + s4[0], y1 = x[u].y * k4[1] + s4[1], y2 = x[u].z * k4[2] + s4[2], y3 = x[u].w * k4[3] + s4[3];
                 if (p.silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-                if (p.drop != nullptr && p.drop->p > 0.f) {
+                if (DROP && p.drop->p > 0.f) {
                     float ds[4];
                     drop_scale4(*p.drop, b, c, pp, C, p.HW, ds);
                     y0 *= ds[0]; y1 *= ds[1]; y2 *= ds[2]; y3 *= ds[3];

@@ -873,10 +873,19 @@ struct sr3_engine {
         REQUIRE(vpp <= 512, "GroupNorm over %d channels is not supported", C);
         const int kpix = vpp >= 256 ? 1 : 256 / vpp;
         const int threads = vpp * kpix;                                // <= 512, every thread owns one 4-channel column
-        int ppb = kpix * 4 * 8;                                        // 8 batches of 4 loads per thread
-        { const int cap = (int)(((long long)p.HW * B) / 1184); if (ppb > cap) ppb = cap; }   // keep ~8 blocks per SM when possible
-        if (ppb < kpix * 4) ppb = kpix * 4;
-        if (ppb > p.HW) ppb = p.HW;
+        // ONE wave of blocks: the kernel uses 64 registers per thread, i.e. 4 resident 256-thread blocks (2 of 512) per SM; a grid sized
+        // for 8 per SM (round 1, 32-register version) runs as two waves and pays the statistics set-up twice (24 vs 15 us on the 128x128
+        // level).  SR3_PREP_SLOTS overrides the number of resident blocks per SM assumed here.
+        int ppb;
+        {
+            const int per_sm = getenv("SR3_PREP_SLOTS") ? atoi(getenv("SR3_PREP_SLOTS")) : (threads > 256 ? 2 : 4);
+            int bpi = per_sm * num_sms() / B; if (bpi < 1) bpi = 1;    // blocks per image
+            const int q = kpix * 4;                                    // 4 loads in flight per thread
+            ppb = (p.HW + bpi - 1) / bpi;
+            ppb = ((ppb + q - 1) / q) * q;
+            if (ppb < q) ppb = q;
+            if (ppb > p.HW) ppb = p.HW;
+        }
         p.pix_per_block = ppb;
         const dim3 grid((p.HW + ppb - 1) / ppb, B);
         const int smem = (2 * C + 2 * groups) * sizeof(float);
@@ -891,7 +900,10 @@ struct sr3_engine {
             m.pix_per_block = mp; m.items_per_image = (p.HW + mp - 1) / mp; m.B = B;
             mega_record(MOP_PREP, m);
         }
-        push([p, grid, smem, threads](cudaStream_t st) { launch_k(prep_kernel, grid, dim3(threads), (size_t)smem, st, p); }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
+        push([p, grid, smem, threads](cudaStream_t st) {
+            if (p.drop) launch_k(prep_kernel<true>, grid, dim3(threads), (size_t)smem, st, p);
+            else launch_k(prep_kernel<false>, grid, dim3(threads), (size_t)smem, st, p);
+        }, 1, 0, (double)B * p.HW * C * (4.0 + 2.0 + (out_raw ? 2.0 : 0.0)));
     }
     void add_cast(const Act& s, bf16* dst, int up) {
         if (dry) return;
@@ -2247,7 +2259,7 @@ int sr3_test_conv_groupnorm(const void* x, const float* w_oihw, const float* bia
     const int kpix = vpp >= 256 ? 1 : 256 / vpp;
     p.pix_per_block = kpix * 4; p.B = B; p.items_per_image = (p.HW + p.pix_per_block - 1) / p.pix_per_block;
     const dim3 grid((p.HW + p.pix_per_block - 1) / p.pix_per_block, B);
-    launch_k(prep_kernel, grid, dim3(vpp * kpix), (size_t)((2 * Cout + 2 * groups) * sizeof(float)), st, p);
+    launch_k(prep_kernel<false>, grid, dim3(vpp * kpix), (size_t)((2 * Cout + 2 * groups) * sizeof(float)), st, p);
     CK(cudaStreamSynchronize(st));
     API_END
 }
