@@ -104,3 +104,81 @@ def test_dgrad_identity_used_by_the_gpu_test():
     (ref,) = torch.autograd.grad(F.conv2d(x, w, None, padding=1), x, dy)
     wp = w.flip(2, 3).transpose(0, 1).contiguous()
     assert torch.allclose(F.conv2d(dy, wp, None, padding=1), ref, atol=1e-5, rtol=1e-5)
+
+
+def test_downsample_dgrad_is_four_parity_phase_convs():
+    """The data gradient of the stride-2 Downsample conv (unet.py:68-74) written as four 2x2-tap convolutions on the low-res dY grid, one per
+    input-pixel parity (py, px) -- the op shape csrc/train_plan.inc `bwd_downsample` hands to the forward tile kernel, with the kernel-row
+    table of pack_down_dgrad_weight_kernel: R(0,0) = none, R(0,1) = 1, R(1,0) = 2, R(1,1) = 0."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 8, 12, generator=g, requires_grad=True)
+    w = torch.randn(7, 5, 3, 3, generator=g)
+    dy = torch.randn(2, 7, 4, 6, generator=g)
+    (ref,) = torch.autograd.grad(F.conv2d(x, w, None, stride=2, padding=1), x, dy)
+    R = {(0, 0): None, (0, 1): 1, (1, 0): 2, (1, 1): 0}
+    dyp = F.pad(dy, (1, 1, 1, 1))                           # taps reach one low-res pixel outside the grid (zero = TMA out-of-bounds fill)
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = torch.zeros(2, 5, 4, 6)
+            for a in range(2):
+                for b in range(2):
+                    r, s = R[(py, a)], R[(px, b)]
+                    if r is None or s is None:
+                        continue
+                    # tap offset (py - 1 + a, px - 1 + b) on the dY grid
+                    sl = dyp[:, :, py + a: py + a + 4, px + b: px + b + 6]
+                    acc += torch.einsum("bohw,oc->bchw", sl, w[:, :, r, s])
+            out[:, :, py::2, px::2] = acc
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_upsample_dgrad_is_one_4x4_stride2_conv():
+    """nearest-2x -> conv3x3 (unet.py:58-65): its data gradient (conv-transpose, then the 2x2 sum of the replicated pixels) equals ONE 4x4
+    stride-2 convolution over dY, dX[i][j] = sum_{u,v} K[u][v] dY[2i-1+u][2j-1+v], K[u][v] = sum over (e, r): e+2-r = u, (f, s): f+2-s = v of
+    W[r][s] -- the kernel pack_up_dgrad_weight_kernel builds and `bwd_upsample` runs through the parity view."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(2, 4, 5, 6, generator=g, requires_grad=True)
+    w = torch.randn(3, 4, 3, 3, generator=g)
+    dy = torch.randn(2, 3, 10, 12, generator=g)
+    (ref,) = torch.autograd.grad(F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, None, padding=1), x, dy)
+    K = torch.zeros(4, 4, 4, 3)                              # [u][v][ci][co]
+    for u in range(4):
+        for v in range(4):
+            for e in range(2):
+                r = e + 2 - u
+                if not 0 <= r <= 2:
+                    continue
+                for f in range(2):
+                    s = f + 2 - v
+                    if 0 <= s <= 2:
+                        K[u, v] += w[:, :, r, s].t()
+    dyp = F.pad(dy, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for u in range(4):
+        for v in range(4):
+            sl = dyp[:, :, u: u + 10: 2, v: v + 12: 2]        # dY[2i-1+u][2j-1+v] with zero padding
+            out += torch.einsum("bohw,co->bchw", sl, K[u, v])
+    assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
+
+
+def test_weight_gradient_is_a_contraction_over_pixels():
+    """dW[co][ci][r][s] = sum_p dY[p][co] X[p + (r-1, s-1)][ci] (zero outside the image): the form wgrad_kernel evaluates with both operands
+    MN-major; also for the stride-2 conv, whose taps read X at (2 oh + r - 1, 2 ow + s - 1)."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(2)
+    for stride in (1, 2):
+        x = torch.randn(2, 4, 8, 8, generator=g)
+        w = torch.randn(5, 4, 3, 3, generator=g, requires_grad=True)
+        oh = 8 // stride
+        dy = torch.randn(2, 5, oh, oh, generator=g)
+        (ref,) = torch.autograd.grad(F.conv2d(x, w, None, stride=stride, padding=1), w, dy)
+        xp = F.pad(x, (1, 1, 1, 1))
+        out = torch.zeros_like(ref)
+        for r in range(3):
+            for s in range(3):
+                sl = xp[:, :, r: r + stride * oh: stride, s: s + stride * oh: stride]
+                out[:, :, r, s] = torch.einsum("bohw,bchw->oc", dy, sl)
+        assert torch.allclose(out, ref, atol=1e-4, rtol=1e-4)
