@@ -102,6 +102,11 @@ def test_no_cpu_fallback_and_unsupported_variants():
         sr3_b200.define_G(opt)
     with pytest.raises(NotImplementedError):
         UNet(with_noise_level_emb=False)
+    # nn.DataParallel (networks.py:113-115) is replaced by one process per GPU: the factory says so instead of wrapping
+    opt = make_opt(FULL, 128)
+    opt["gpu_ids"], opt["distributed"] = [0, 1], True
+    with pytest.raises(NotImplementedError, match="parallel"):
+        sr3_b200.define_G(opt)
 
 
 def test_q_sample_and_helpers_match_oracle():
