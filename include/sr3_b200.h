@@ -49,9 +49,9 @@ int sr3_abi_version(void);
 
 /* UNet.__init__ (model/sr3_modules/unet.py:161-233) + GaussianDiffusion.__init__ (diffusion.py:64-82):
  * builds the layer plan, allocates activations / packed weights on `device` for a fixed batch size.
- * Threading: calls on one engine must be serialised by the caller.  Kernels that wait for partner CTAs (the persistent step kernel's grid
- * barriers, split-K tile launches of the per-layer path) are launched cooperatively, so engines driven concurrently from different
- * streams of one device serialise instead of deadlocking. */
+ * Threading: calls on one engine must be serialised by the caller.  Kernels whose CTAs wait for partners are safe next to other work on the
+ * device: the split-K partners of a tile are one thread-block cluster (gang-scheduled by the hardware), the persistent step kernel (SR3_MEGA=1)
+ * is a cooperative launch -- engines driven concurrently from different streams of one device cannot deadlock each other. */
 int sr3_engine_create(const sr3_unet_config* cfg, int batch, int device, sr3_engine** out);
 void sr3_engine_destroy(sr3_engine* e);
 
