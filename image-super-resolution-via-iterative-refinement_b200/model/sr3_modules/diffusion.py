@@ -50,9 +50,11 @@ class _PLossesFn(torch.autograd.Function):
     def forward(ctx, module, eng, hr, sr, gamma, noise, seed, *params):
         loss = eng.train_forward(hr, sr, gamma, noise, module.loss_type, seed)
         ctx.eng = eng
-        ctx.names = [n for n, _ in eng.param_table()]
-        by_name = dict(module.denoise_fn.named_parameters())
-        ctx.order = [by_name[n] for n in ctx.names]
+        order = getattr(eng, "_param_order", None)          # parameters in the engine's (= the reference's state_dict) order, cached per engine
+        if order is None:
+            by_name = dict(module.denoise_fn.named_parameters())
+            order = eng._param_order = [by_name[n] for n, _ in eng.param_table()]
+        ctx.order = order
         ctx.params = params
         return torch.tensor(loss, dtype=torch.float32, device=hr.device)
 
