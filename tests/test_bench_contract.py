@@ -31,3 +31,17 @@ def test_reference_arm_other_ranks_are_silent():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == "", (r.stdout, r.stderr[-500:])
+
+
+def test_training_reference_arm_prints_one_json_line():
+    """--workload train --impl reference: the unmodified reference's optimize_parameters arithmetic on a bounded sample of the batch."""
+    env = dict(os.environ, OMP_NUM_THREADS=os.environ.get("OMP_NUM_THREADS", "8"))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "train", "--gpus", "1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=900, env=env, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.strip().splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "steps/s" and d["metric"].startswith("training steps/sec") and d["value"] > 0
+    assert d["config"]["global_batch"] == 64 and "scaled by 32" in d["cpu_baseline"]["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
